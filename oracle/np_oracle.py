@@ -1,0 +1,289 @@
+"""oracle/np_oracle.py -- TEST INFRASTRUCTURE ONLY (second, independent CPU oracle + CPU baseline).
+
+numpy/einsum restatement of the post-HF hot path of ajay-mk/QC-P2, written from the
+equations the reference cites (Stanton, Gauss, Watts, Bartlett, JCP 94, 4334 (1991)
+eqs. 1-13; Crawford ProgrammingProjects #6 for (T)) rather than from oracle.cpp, so the two
+oracles check each other.  Reference call sites: src/integrals.cpp:95-207,
+src/mp2.cpp:11-42, src/cc.cpp:125-560.
+
+PARITY UNPINNED against the reference binary (it cannot be built here and ships no golden
+vectors); pinned only to the external Crawford water/STO-3G numbers.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.
+"""
+import itertools
+
+import numpy as np
+
+MASK64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+# --------------------------------------------------------------------------------------
+# counter-based synthetic data (same generator as csrc/synth.cu)
+# --------------------------------------------------------------------------------------
+def splitmix64(x):
+    x = np.asarray(x, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = x + np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def u_rand(seed, tag, idx):
+    """u(tag, idx) in [-1, 1): (splitmix64(seed ^ tag<<56 ^ idx) >> 11) * 2^-52 - 1."""
+    key = np.uint64(seed) ^ (np.uint64(tag) << np.uint64(56))
+    z = splitmix64(np.asarray(idx, dtype=np.uint64) ^ key)
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 ** -52) - 1.0
+
+
+TAG_T1, TAG_T2, TAG_OOVV, TAG_VOVV, TAG_OVOO = 1, 2, 3, 4, 5
+SEED = 20261019
+
+
+def _antisym_pair_fill(shape, tag, scale, seed, pair):
+    """Dense tensor with values scale*u(tag, linear index of the canonical element) placed on
+    canonical (p<q) positions of the index pair `pair` and extended antisymmetrically."""
+    idx = np.arange(int(np.prod(shape)), dtype=np.uint64).reshape(shape)
+    base = scale * u_rand(seed, tag, idx)
+    p, q = pair
+    ip = np.arange(shape[p]).reshape([-1 if d == p else 1 for d in range(len(shape))])
+    iq = np.arange(shape[q]).reshape([-1 if d == q else 1 for d in range(len(shape))])
+    upper = np.where(ip < iq, base, 0.0)
+    return upper - np.swapaxes(upper, p, q)
+
+
+def synthetic_t_inputs(o, v, seed=SEED):
+    """Antisymmetrised random (T) inputs of SURVEY.md section 8d (config 5 generator)."""
+    T1 = 0.05 * u_rand(seed, TAG_T1, np.arange(o * v, dtype=np.uint64)).reshape(o, v)
+
+    def two_pair(tag, scale):
+        shape = (o, o, v, v)
+        idx = np.arange(o * o * v * v, dtype=np.uint64).reshape(shape)
+        base = scale * u_rand(seed, tag, idx)
+        i = np.arange(o).reshape(-1, 1, 1, 1)
+        j = np.arange(o).reshape(1, -1, 1, 1)
+        a = np.arange(v).reshape(1, 1, -1, 1)
+        b = np.arange(v).reshape(1, 1, 1, -1)
+        c = np.where((i < j) & (a < b), base, 0.0)
+        c = c - c.transpose(1, 0, 2, 3)
+        return c - c.transpose(0, 1, 3, 2)
+
+    T2 = two_pair(TAG_T2, 0.02)
+    oovv = two_pair(TAG_OOVV, 0.1)
+    vovv = _antisym_pair_fill((v, o, v, v), TAG_VOVV, 0.1, seed, (2, 3))
+    ovoo = _antisym_pair_fill((o, v, o, o), TAG_OVOO, 0.1, seed, (2, 3))
+    eo = -2.0 + 1.5 * np.arange(o) / max(o - 1, 1)
+    ev = 0.1 + 2.9 * np.arange(v) / max(v - 1, 1)
+    return dict(T1=T1, T2=T2, oovv=oovv, vovv=vovv, ovoo=ovoo, eps_o=eo, eps_v=ev)
+
+
+# --------------------------------------------------------------------------------------
+# integrals.cpp / mp2.cpp
+# --------------------------------------------------------------------------------------
+def transform_ao_mo(ao, C1, C2):
+    """(pq|rs) -> (ij|kl): k,l rotated by C1, i,j by C2 (integrals.cpp:121-129)."""
+    return np.einsum("pqrs,pi,qj,rk,sl->ijkl", ao, C2, C2, C1, C1, optimize=True)
+
+
+def transform_to_so(aa, bb, ab):
+    """integrals.cpp:136-167, including the as-written alpha/beta label use."""
+    n = aa.shape[0]
+    so = np.zeros((2 * n,) * 4)
+    A, B = slice(0, None, 2), slice(1, None, 2)
+    phys = lambda t: t.transpose(0, 2, 1, 3)  # t[I,K,J,L] -> [I,J,K,L]
+    so[A, A, A, A] = phys(aa) - phys(aa).transpose(1, 0, 2, 3)
+    so[B, B, B, B] = phys(bb) - phys(bb).transpose(1, 0, 2, 3)
+    so[A, B, A, B] = phys(ab)                      # i a, k a, j b, l b
+    so[B, A, B, A] = phys(ab)                      # i b, k b, j a, l a
+    so[B, A, A, B] = -phys(ab).transpose(1, 0, 2, 3)  # -(ab)[J,K,I,L]
+    so[A, B, B, A] = -phys(ab).transpose(1, 0, 2, 3)
+    return so
+
+
+def slice_ints(so, no, spec):
+    sl = [slice(0, no) if c == "o" else slice(no, None) for c in spec]
+    return np.ascontiguousarray(so[tuple(sl)])
+
+
+INT_NAMES = ["oooo", "ovoo", "oovo", "ooov", "ovov", "ovvo", "oovv", "vovv", "ovvv", "vvvo", "vvvv"]
+
+
+def get_integrals(so, no):
+    return {k: slice_ints(so, no, k) for k in INT_NAMES}
+
+
+def mp2(oovv, eo, ev):
+    D = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
+    return oovv / D, 0.25 * np.sum(oovv * oovv / D)
+
+
+# --------------------------------------------------------------------------------------
+# cc.cpp: CCSD (Stanton 1991), written with physicists' einsum
+# --------------------------------------------------------------------------------------
+def _taus(t1, t2):
+    tt = np.einsum("ia,jb->ijab", t1, t1)
+    tt = tt - tt.transpose(0, 1, 3, 2)
+    return t2 + tt, t2 + 0.5 * tt
+
+
+def intermediates(t1, t2, I, foo, fov, fvv):
+    tau, taub = _taus(t1, t2)
+    offd = lambda f: f - np.diag(np.diag(f))
+    Fae = offd(fvv) - 0.5 * np.einsum("me,ma->ae", fov, t1) + np.einsum("mf,mafe->ae", t1, I["ovvv"]) \
+        - 0.5 * np.einsum("mnaf,mnef->ae", taub, I["oovv"])
+    Fmi = offd(foo) + 0.5 * np.einsum("ie,me->mi", t1, fov) + np.einsum("ne,mnie->mi", t1, I["ooov"]) \
+        + 0.5 * np.einsum("inef,mnef->mi", taub, I["oovv"])
+    Fme = fov + np.einsum("nf,mnef->me", t1, I["oovv"])
+    Wmnij = I["oooo"] + np.einsum("je,mnie->mnij", t1, I["ooov"]) - np.einsum("ie,mnje->mnij", t1, I["ooov"]) \
+        + 0.25 * np.einsum("ijef,mnef->mnij", tau, I["oovv"])
+    Wabef = I["vvvv"] - np.einsum("mb,amef->abef", t1, I["vovv"]) + np.einsum("ma,bmef->abef", t1, I["vovv"]) \
+        + 0.25 * np.einsum("mnab,mnef->abef", tau, I["oovv"])
+    Wmbej = I["ovvo"] + np.einsum("jf,mbef->mbej", t1, I["ovvv"]) - np.einsum("nb,mnej->mbej", t1, I["oovo"]) \
+        - np.einsum("jnfb,mnef->mbej", 0.5 * t2 + np.einsum("jf,nb->jnfb", t1, t1), I["oovv"])
+    return dict(F_ae=Fae, F_mi=Fmi, F_me=Fme, W_mnij=Wmnij, W_mbej=Wmbej, W_abef=Wabef)
+
+
+def new_T1(t1, t2, I, X, fov, eo, ev):
+    r = fov + np.einsum("ie,ae->ia", t1, X["F_ae"]) - np.einsum("ma,mi->ia", t1, X["F_mi"]) \
+        + np.einsum("imae,me->ia", t2, X["F_me"]) - np.einsum("nf,naif->ia", t1, I["ovov"]) \
+        - 0.5 * np.einsum("imef,maef->ia", t2, I["ovvv"]) - 0.5 * np.einsum("mnae,nmei->ia", t2, I["oovo"])
+    return r / (eo[:, None] - ev[None, :])
+
+
+def new_T2(t1, t2, I, X, eo, ev):
+    tau, _ = _taus(t1, t2)
+    Pab = lambda x: x - x.transpose(0, 1, 3, 2)
+    Pij = lambda x: x - x.transpose(1, 0, 2, 3)
+    r = I["oovv"].copy()
+    r += Pab(np.einsum("ijae,be->ijab", t2, X["F_ae"] - 0.5 * np.einsum("mb,me->be", t1, X["F_me"])))
+    r -= Pij(np.einsum("imab,mj->ijab", t2, X["F_mi"] + 0.5 * np.einsum("je,me->mj", t1, X["F_me"])))
+    r += 0.5 * np.einsum("mnab,mnij->ijab", tau, X["W_mnij"])
+    r += 0.5 * np.einsum("ijef,abef->ijab", tau, X["W_abef"])
+    r += Pij(Pab(np.einsum("imae,mbej->ijab", t2, X["W_mbej"])
+                 - np.einsum("ie,ma,mbej->ijab", t1, t1, I["ovvo"])))
+    r += Pij(np.einsum("ie,abej->ijab", t1, I["vvvo"]))
+    r -= Pab(np.einsum("ma,mbij->ijab", t1, I["ovoo"]))
+    D = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
+    return r / D
+
+
+def ccsd_energy(t1, t2, oovv, fov):
+    return np.sum(fov * t1) + 0.25 * np.sum(oovv * t2) + 0.5 * np.einsum("ijab,ia,jb->", oovv, t1, t1)
+
+
+def ccsd(I, foo, fov, fvv, t2_guess, maxiter, conv):
+    """cc.cpp:409-451 trajectory: E before update; new T1 feeds new_T2 with old intermediates."""
+    eo, ev = np.diag(foo).copy(), np.diag(fvv).copy()
+    t1 = np.zeros(fov.shape)
+    t2 = t2_guess.copy()
+    e_last, hist = 0.0, []
+    for it in range(maxiter):
+        e = ccsd_energy(t1, t2, I["oovv"], fov)
+        hist.append(e)
+        if abs(e - e_last) < conv:
+            break
+        e_last = e
+        X = intermediates(t1, t2, I, foo, fov, fvv)
+        t1 = new_T1(t1, t2, I, X, fov, eo, ev)
+        t2 = new_T2(t1, t2, I, X, eo, ev)
+    return t1, t2, hist
+
+
+# note on new_T2's "- t_ie t_ma <mb||ej>" term: cc.cpp:360-363 contracts (t_ie t_ma) with
+# ovov{m,b,j,e}; <mb||je> = -<mb||ej>, so +ovov there equals -ovvo here.  Only valid when
+# the integrals are antisymmetric in the ket (true for RHF inputs, not for the as-written UHF
+# path), so tests that use this module for UHF-as-written compare against oracle.cpp instead.
+
+
+# --------------------------------------------------------------------------------------
+# cc.cpp:454-560: (T)
+# --------------------------------------------------------------------------------------
+def ccsd_t_einsum(T1, T2, oovv, vovv, ovoo, eo, ev):
+    """Crawford project #6 formulas, dense o^3 v^3 (small sizes only)."""
+    o, v = T1.shape
+
+    def perm_abc(x):  # P(a/bc): x - (a<->b) - (a<->c)
+        return x - x.transpose(0, 1, 2, 4, 3, 5) - x.transpose(0, 1, 2, 5, 4, 3)
+
+    def perm_ijk(x):  # P(i/jk)
+        return x - x.transpose(1, 0, 2, 3, 4, 5) - x.transpose(2, 1, 0, 3, 4, 5)
+
+    Dd = perm_ijk(perm_abc(np.einsum("ia,jkbc->ijkabc", T1, oovv)))
+    part = np.einsum("jkae,eibc->ijkabc", T2, vovv) - np.einsum("imbc,majk->ijkabc", T2, ovoo)
+    Dc = perm_ijk(perm_abc(part))
+    D = (eo[:, None, None, None, None, None] + eo[None, :, None, None, None, None]
+         + eo[None, None, :, None, None, None] - ev[None, None, None, :, None, None]
+         - ev[None, None, None, None, :, None] - ev[None, None, None, None, None, :])
+    return np.sum(Dc * (Dc + Dd) / D) / 36.0
+
+
+def sorted_triples(o):
+    return np.array(list(itertools.combinations(range(o), 3)), dtype=np.int32).reshape(-1, 3)
+
+
+def all_triples(o):
+    return np.array(list(itertools.product(range(o), repeat=3)), dtype=np.int32).reshape(-1, 3)
+
+
+def ccsd_t_triple_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k):
+    """One occupied triple via the single-GEMM restatement:
+    X = A.B, K = 3(v+o); W = X - X[b,a,c] - X[c,b,a]; returns sum_abc W (W+V)/D (no 1/36)."""
+    o, v = T1.shape
+    A = np.concatenate([T2[j, k], -T2[i, k], -T2[j, i],
+                        -ovoo[:, :, j, k].T, ovoo[:, :, i, k].T, ovoo[:, :, j, i].T], axis=1)
+    B = np.concatenate([vovv[:, i].reshape(v, v * v), vovv[:, j].reshape(v, v * v), vovv[:, k].reshape(v, v * v),
+                        T2[i].reshape(o, v * v), T2[j].reshape(o, v * v), T2[k].reshape(o, v * v)], axis=0)
+    X = (A @ B).reshape(v, v, v)
+    W = X - X.transpose(1, 0, 2) - X.transpose(2, 1, 0)
+    Y = (np.einsum("a,bc->abc", T1[i], oovv[j, k]) - np.einsum("a,bc->abc", T1[j], oovv[i, k])
+         - np.einsum("a,bc->abc", T1[k], oovv[j, i]))
+    V = Y - Y.transpose(1, 0, 2) - Y.transpose(2, 1, 0)
+    D = eo[i] + eo[j] + eo[k] - ev[:, None, None] - ev[None, :, None] - ev[None, None, :]
+    return float(np.sum(W * (W + V) / D))
+
+
+def ccsd_t_blocked(T1, T2, oovv, vovv, ovoo, eo, ev, symmetric):
+    """Full E(T) triple by triple.  symmetric=True: i<j<k only, weight 6 (needs antisymmetric
+    inputs); False: all o^3 ordered triples (literal sum)."""
+    o = T1.shape[0]
+    trip = sorted_triples(o) if symmetric else all_triples(o)
+    w = 6.0 if symmetric else 1.0
+    e = 0.0
+    for (i, j, k) in trip:
+        e += w * ccsd_t_triple_np(T1, T2, oovv, vovv, ovoo, eo, ev, int(i), int(j), int(k))
+    return e / 36.0
+
+
+def ccsd_t_triple_packed_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k, bu=None, cu=None):
+    """CPU baseline kernel for config 5: one i<j<k triple with b<c column packing
+    (M=v, N=v(v-1)/2, K=3(v+o) GEMM via BLAS) and the a<b<c energy sum; returns the triple's
+    contribution to E(T) (already including the 6*6/36 weight)."""
+    o, v = T1.shape
+    if bu is None:
+        bu, cu = np.triu_indices(v, 1)
+    A = np.concatenate([T2[j, k], -T2[i, k], -T2[j, i],
+                        -ovoo[:, :, j, k].T, ovoo[:, :, i, k].T, ovoo[:, :, j, i].T], axis=1)
+    B = np.concatenate([vovv[:, i][:, bu, cu], vovv[:, j][:, bu, cu], vovv[:, k][:, bu, cu],
+                        T2[i][:, bu, cu], T2[j][:, bu, cu], T2[k][:, bu, cu]], axis=0)
+    Xp = A @ B  # [v, NP]
+    X = np.zeros((v, v, v))
+    X[:, bu, cu] = Xp
+    X[:, cu, bu] = -Xp
+    W = X - X.transpose(1, 0, 2) - X.transpose(2, 1, 0)
+    Y = (np.einsum("a,bc->abc", T1[i], oovv[j, k]) - np.einsum("a,bc->abc", T1[j], oovv[i, k])
+         - np.einsum("a,bc->abc", T1[k], oovv[j, i]))
+    V = Y - Y.transpose(1, 0, 2) - Y.transpose(2, 1, 0)
+    D = eo[i] + eo[j] + eo[k] - ev[:, None, None] - ev[None, :, None] - ev[None, None, :]
+    a, b, c = np.meshgrid(np.arange(v), np.arange(v), np.arange(v), indexing="ij")
+    m = (a < b) & (b < c)
+    return float(np.sum((W * (W + V) / D)[m]))
+
+
+def t_flops(o, v, ntriples=None):
+    """Algorithmic flop count of SURVEY.md section 8d: one M=v, N=v(v-1)/2, K=3(v+o) GEMM per triple."""
+    if ntriples is None:
+        ntriples = o * (o - 1) * (o - 2) // 6
+    return ntriples * 2.0 * v * (v * (v - 1) // 2) * 3 * (v + o)

@@ -1,0 +1,600 @@
+// api.cu -- the C ABI of include/qcp2_b200.h: argument checking, host<->device marshalling
+// for QCP2_HOST pointer mode, exception -> status translation.  No arithmetic happens here
+// and there is no CPU path: every entry point ends in kernels on the context's device.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/qcp2_b200.h"
+#include "contract.cuh"
+#include "dgemm.cuh"
+#include "post_hf.cuh"
+#include "tensor_ops.cuh"
+#include "triples.cuh"
+
+using namespace qcp2;
+
+struct qcp2_ctx {
+    Ctx c;
+};
+struct qcp2_t_plan {
+    qcp2_ctx *owner = nullptr;
+    std::unique_ptr<TPlan> plan;
+};
+
+namespace {
+
+// device view of an input tensor: pass-through in device mode, staged copy in host mode
+struct In {
+    DBuf buf;
+    const double *p = nullptr;
+    In() {}
+    In(Ctx &c, const double *src, long long n) {
+        if (!src) return;
+        if (c.pointer_mode == QCP2_DEVICE) {
+            p = src;
+        } else {
+            buf = DBuf(c, (size_t) std::max<long long>(n, 1));
+            if (n > 0) QCP2_CUDA(cudaMemcpyAsync(buf.p, src, (size_t) n * 8, cudaMemcpyHostToDevice, c.stream));
+            p = buf.p;
+        }
+    }
+    operator const double *() const { return p; }
+};
+// device view of an output tensor; finish() copies back in host mode
+struct Out {
+    Ctx *c = nullptr;
+    DBuf buf;
+    double *p = nullptr, *host = nullptr;
+    long long n = 0;
+    Out() {}
+    Out(Ctx &ctx, double *dst, long long n_) : c(&ctx), n(n_) {
+        if (!dst) return;
+        if (ctx.pointer_mode == QCP2_DEVICE) p = dst;
+        else buf = DBuf(ctx, (size_t) std::max<long long>(n_, 1)), p = buf.p, host = dst;
+    }
+    void finish() {
+        if (host && n > 0) QCP2_CUDA(cudaMemcpyAsync(host, p, (size_t) n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    operator double *() const { return p; }
+};
+
+template<class F>
+int guarded(qcp2_ctx *ctx, F &&f) {
+    if (!ctx) return 2;
+    try {
+        QCP2_CUDA(cudaSetDevice(ctx->c.device));
+        f(ctx->c);
+        return 0;
+    } catch (const std::exception &e) {
+        ctx->c.last_error = e.what();
+        return 1;
+    }
+}
+
+long long ipow4(long long n) { return n * n * n * n; }
+
+}// namespace
+
+extern "C" {
+
+const char *qcp2_version(void) { return "qcp2_b200 0.1 (sm_100a, DMMA.8x8x4)"; }
+
+int qcp2_create(int device, qcp2_ctx **out) {
+    if (!out) return 2;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return 3;// no CUDA device: there is deliberately no CPU fallback
+    }
+    if (device < 0 || device >= ndev) return 4;
+    std::unique_ptr<qcp2_ctx> ctx(new qcp2_ctx());
+    try {
+        QCP2_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        QCP2_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) throw Error("qcp2_b200 requires an sm_100a device (B200)");
+        ctx->c.device = device;
+        ctx->c.sm_count = prop.multiProcessorCount;
+        QCP2_CUDA(cudaStreamCreateWithFlags(&ctx->c.own_stream, cudaStreamNonBlocking));
+        ctx->c.stream = ctx->c.own_stream;
+        cudaMemPool_t pool;
+        QCP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ULL;// keep freed workspace cached in the pool
+        QCP2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    } catch (const std::exception &e) {
+        fprintf(stderr, "qcp2_create: %s\n", e.what());
+        return 1;
+    }
+    *out = ctx.release();
+    return 0;
+}
+
+int qcp2_destroy(qcp2_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.own_stream);
+    delete ctx;
+    return 0;
+}
+
+int qcp2_set_pointer_mode(qcp2_ctx *ctx, int mode) {
+    if (!ctx || (mode != QCP2_HOST && mode != QCP2_DEVICE)) return 2;
+    ctx->c.pointer_mode = mode;
+    return 0;
+}
+int qcp2_set_stream(qcp2_ctx *ctx, void *stream) {
+    if (!ctx) return 2;
+    ctx->c.stream = stream ? static_cast<cudaStream_t>(stream) : ctx->c.own_stream;
+    return 0;
+}
+int qcp2_synchronize(qcp2_ctx *ctx) {
+    return guarded(ctx, [&](Ctx &c) { c.sync(); });
+}
+const char *qcp2_last_error(const qcp2_ctx *ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
+long long qcp2_kernel_launches(const qcp2_ctx *ctx) { return ctx ? ctx->c.launches : 0; }
+
+// ---- integrals.h ------------------------------------------------------------------
+int qcp2_transform_ao_mo(qcp2_ctx *ctx, const double *pq_rs, const double *C1, const double *C2, int n, double *out) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(pq_rs && C1 && C2 && out && n >= 1, "transform_ao_mo: null argument or n < 1");
+        const long long n4 = ipow4(n);
+        In ao(c, pq_rs, n4), c1(c, C1, (long long) n * n), c2(c, C2, (long long) n * n);
+        Out o(c, out, n4);
+        transform_ao_mo_dev(c, ao, c1, c2, n, o);
+        o.finish();
+        c.sync();
+    });
+}
+
+int qcp2_transform_to_so(qcp2_ctx *ctx, const double *aa, const double *bb, const double *ab, int n, double *so) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(aa && bb && ab && so && n >= 1, "transform_to_so: null argument or n < 1");
+        const long long n4 = ipow4(n);
+        In a(c, aa, n4);
+        In b = (bb == aa) ? In() : In(c, bb, n4);
+        In x = (ab == aa) ? In() : (ab == bb ? In() : In(c, ab, n4));
+        const double *pb = (bb == aa) ? a.p : b.p;
+        const double *px = (ab == aa) ? a.p : (ab == bb ? pb : x.p);
+        Out o(c, so, 16 * n4);
+        to_so(c, a, pb, px, n, o);
+        o.finish();
+        c.sync();
+    });
+}
+
+int qcp2_slice_ints(qcp2_ctx *ctx, const double *so, int n2, int o, int v, const char *spec, double *out) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(so && out && spec && strlen(spec) == 4, "slice_ints: bad argument");
+        long long n = 1;
+        for (int d = 0; d < 4; ++d) n *= spec[d] == 'o' ? o : v;
+        In s(c, so, ipow4(n2));
+        Out r(c, out, n);
+        slice_block(c, s, n2, o, v, spec, r);
+        r.finish();
+        c.sync();
+    });
+}
+
+int qcp2_make_denom(qcp2_ctx *ctx, const double *F_spin, int n2, int o, int v, double *denom) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(F_spin && denom && o + v <= n2, "make_denom: bad argument");
+        In f(c, F_spin, (long long) n2 * n2);
+        Out d(c, denom, (long long) o * o * v * v);
+        make_denom(c, f, n2, o, v, d);
+        d.finish();
+        c.sync();
+    });
+}
+
+// ---- mp2.h ------------------------------------------------------------------------
+int qcp2_make_so_moes(qcp2_ctx *ctx, const double *ea, const double *eb, int n, double *F) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(ea && eb && F && n >= 1, "make_so_moes: bad argument");
+        In a(c, ea, n), b(c, eb, n);
+        Out f(c, F, 4LL * n * n);
+        make_so_moes(c, a, b, n, f);
+        f.finish();
+        c.sync();
+    });
+}
+
+int qcp2_run_mp2(qcp2_ctx *ctx, const double *oovv, const double *denom, int o, int v, double *T, double *energy) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(oovv && denom && energy, "run_mp2: null argument");
+        const long long n = (long long) o * o * v * v;
+        In g(c, oovv, n), d(c, denom, n);
+        Out t(c, T, n);
+        DBuf e(c, 1);
+        mp2_amplitudes_energy(c, g, d, n, t, e);
+        t.finish();
+        QCP2_CUDA(cudaMemcpyAsync(energy, e.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+int qcp2_mp2(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
+             const double *eps_b, int n, int o, int v, int uhf, double *so_ints, double *T, double *energy) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(ao_ints && Ca && eps_a && energy && n >= 1, "MP2: null argument");
+        if (uhf) QCP2_REQUIRE(Cb && eps_b, "MP2: UHF needs Cb and eps_b");
+        const long long n4 = ipow4(n);
+        In ao(c, ao_ints, n4), ca(c, Ca, (long long) n * n), ea(c, eps_a, n);
+        In cb = uhf ? In(c, Cb, (long long) n * n) : In();
+        In eb = uhf ? In(c, eps_b, n) : In();
+        Out so(c, so_ints, 16 * n4), t(c, T, (long long) o * o * v * v);
+        mp2_dev(c, ao, ca, uhf ? cb.p : ca.p, ea, uhf ? eb.p : ea.p, n, o, v, uhf != 0, so, t, energy);
+        so.finish(), t.finish();
+        c.sync();
+    });
+}
+
+// ---- cc.h -------------------------------------------------------------------------
+int qcp2_make_fock(qcp2_ctx *ctx, const double *e1, const double *e2, int n1, int n2, double *F) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(e1 && e2 && F && n2 > n1 && n1 >= 0, "make_fock: bad argument");
+        const long long need = n1 / 2 + (n2 - n1 - 1) / 2 + (n1 % 2) + 1;// highest eps index read, cc.cpp:28-31
+        In a(c, e1, need), b(c, e2, need);
+        Out f(c, F, (long long) (n2 - n1) * (n2 - n1));
+        make_fock(c, a, b, n1, n2, f);
+        f.finish();
+        c.sync();
+    });
+}
+
+int qcp2_make_tau(qcp2_ctx *ctx, const double *Ts, const double *Td, int o, int v, int bar, double *tau) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(Ts && Td && tau, "make_tau: null argument");
+        const long long n = (long long) o * o * v * v;
+        In ts(c, Ts, (long long) o * v), td(c, Td, n);
+        Out t(c, tau, n);
+        make_tau(c, ts, td, o, v, bar != 0, t);
+        t.finish();
+        c.sync();
+    });
+}
+
+int qcp2_multiply_Ts(qcp2_ctx *ctx, const double *Ts, int o, int v, double *out) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(Ts && out, "multiply_Ts: null argument");
+        In ts(c, Ts, (long long) o * v);
+        Out t(c, out, (long long) o * v * o * v);
+        multiply_Ts(c, ts, o, v, t);
+        t.finish();
+        c.sync();
+    });
+}
+
+static int make_D(qcp2_ctx *ctx, const double *f_oo, const double *f_vv, int o, int v, double *D, int which) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(f_oo && f_vv && D, "make_D: null argument");
+        const long long O = o, V = v;
+        const long long n = which == 1 ? O * V : (which == 2 ? O * O * V * V : O * O * O * V * V * V);
+        In foo(c, f_oo, O * O), fvv(c, f_vv, V * V);
+        Out d(c, D, n);
+        if (which == 1) make_D_ia(c, foo, fvv, o, v, d);
+        else if (which == 2) make_D_ijab(c, foo, fvv, o, v, d);
+        else make_D_triples(c, foo, fvv, o, v, d);
+        d.finish();
+        c.sync();
+    });
+}
+int qcp2_make_D_ia(qcp2_ctx *ctx, const double *f_oo, const double *f_vv, int o, int v, double *D) {
+    return make_D(ctx, f_oo, f_vv, o, v, D, 1);
+}
+int qcp2_make_D_ijab(qcp2_ctx *ctx, const double *f_oo, const double *f_vv, int o, int v, double *D) {
+    return make_D(ctx, f_oo, f_vv, o, v, D, 2);
+}
+int qcp2_make_D_triples(qcp2_ctx *ctx, const double *f_oo, const double *f_vv, int o, int v, double *D) {
+    return make_D(ctx, f_oo, f_vv, o, v, D, 3);
+}
+
+namespace {
+struct IntsIn {
+    In in[I_COUNT];
+    IntsDev dev;
+    IntsIn(Ctx &c, const double *const *ints, int o, int v, unsigned need_mask) {
+        for (int k = 0; k < I_COUNT; ++k) {
+            dev.p[k] = nullptr;
+            if (!ints[k]) {
+                QCP2_REQUIRE(!(need_mask & (1u << k)), std::string("missing integral block ") + kIntNames[k]);
+                continue;
+            }
+            if (!(need_mask & (1u << k)) && c.pointer_mode == QCP2_HOST) continue;// do not upload what is not read
+            in[k] = In(c, ints[k], int_block_size(k, o, v));
+            dev.p[k] = in[k].p;
+        }
+    }
+};
+struct InterIO {
+    In in[X_COUNT];
+    Out out[X_COUNT];
+    InterDev dev;
+};
+constexpr unsigned bit(int k) { return 1u << k; }
+constexpr unsigned kNeedInter = bit(I_OOOO) | bit(I_OOOV) | bit(I_OOVO) | bit(I_OOVV) | bit(I_VOVV) | bit(I_OVVV) |
+                                bit(I_VVVV) | bit(I_OVVO);
+constexpr unsigned kNeedT1 = bit(I_OVOV) | bit(I_OVVV) | bit(I_OOVO);
+constexpr unsigned kNeedT2 = bit(I_OOVV) | bit(I_OVOV) | bit(I_VVVO) | bit(I_OVOO);
+constexpr unsigned kNeedAll = (1u << I_COUNT) - 1;
+}// namespace
+
+int qcp2_update_intermediates(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
+                              const double *f_oo, const double *f_ov, const double *f_vv, int o, int v,
+                              double *const *inter) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(Ts && Td && ints && f_oo && f_vv && inter, "update_intermediates: null argument");
+        const long long O = o, V = v;
+        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fov(c, f_ov, O * V), fvv(c, f_vv, V * V);
+        IntsIn I(c, ints, o, v, kNeedInter);
+        Out outs[X_COUNT];
+        InterDev X;
+        for (int k = 0; k < X_COUNT; ++k) {
+            QCP2_REQUIRE(inter[k], "update_intermediates: null output block");
+            outs[k] = Out(c, inter[k], inter_block_size(k, o, v));
+            X.p[k] = outs[k].p;
+        }
+        update_intermediates_dev(c, ts, td, I.dev, foo, f_ov ? fov.p : nullptr, fvv, o, v, X);
+        for (int k = 0; k < X_COUNT; ++k) outs[k].finish();
+        c.sync();
+    });
+}
+
+int qcp2_make_T1(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
+                 const double *const *inter, const double *f_oo, const double *f_ov, const double *f_vv, int o, int v,
+                 double *T1_new) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(Ts && Td && ints && inter && f_oo && f_vv && T1_new, "make_T1: null argument");
+        const long long O = o, V = v;
+        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fov(c, f_ov, O * V), fvv(c, f_vv, V * V);
+        IntsIn I(c, ints, o, v, kNeedT1);
+        In xin[X_COUNT];
+        InterDev X;
+        for (int k = 0; k < X_COUNT; ++k) {
+            X.p[k] = nullptr;
+            if (k == X_FAE || k == X_FMI || k == X_FME) {
+                QCP2_REQUIRE(inter[k], "make_T1: missing intermediate");
+                xin[k] = In(c, inter[k], inter_block_size(k, o, v));
+                X.p[k] = const_cast<double *>(xin[k].p);
+            }
+        }
+        Out t(c, T1_new, O * V);
+        make_T1_dev(c, ts, td, I.dev, X, foo, f_ov ? fov.p : nullptr, fvv, o, v, t);
+        t.finish();
+        c.sync();
+    });
+}
+
+int qcp2_make_T2(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
+                 const double *const *inter, const double *f_oo, const double *f_vv, int o, int v, double *T2_new) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(Ts && Td && ints && inter && f_oo && f_vv && T2_new, "make_T2: null argument");
+        const long long O = o, V = v;
+        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fvv(c, f_vv, V * V);
+        IntsIn I(c, ints, o, v, kNeedT2);
+        In xin[X_COUNT];
+        InterDev X;
+        for (int k = 0; k < X_COUNT; ++k) {
+            QCP2_REQUIRE(inter[k], "make_T2: missing intermediate");
+            xin[k] = In(c, inter[k], inter_block_size(k, o, v));
+            X.p[k] = const_cast<double *>(xin[k].p);
+        }
+        Out t(c, T2_new, O * O * V * V);
+        make_T2_dev(c, ts, td, I.dev, X, foo, fvv, o, v, t);
+        t.finish();
+        c.sync();
+    });
+}
+
+int qcp2_ccsd_energy(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *oovv, const double *f_ov, int o,
+                     int v, double *energy) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(Ts && Td && oovv && energy, "ccsd_energy: null argument");
+        const long long O = o, V = v;
+        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), g(c, oovv, O * O * V * V), fov(c, f_ov, O * V);
+        DBuf e(c, 1);
+        ccsd_energy(c, ts, td, g, f_ov ? fov.p : nullptr, o, v, e);
+        QCP2_CUDA(cudaMemcpyAsync(energy, e.p, 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+int qcp2_ccsd(qcp2_ctx *ctx, const double *so_ints, int n2, const double *const *ints, const double *f_oo,
+              const double *f_ov, const double *f_vv, const double *T2_guess, int o, int v, int maxiter, double conv,
+              double *T1, double *T2, double *energy, int *iters, double *e_hist, double *const *sliced_out) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE((so_ints || ints) && f_oo && f_vv && T2_guess && T1 && T2 && energy, "CCSD: null argument");
+        QCP2_REQUIRE(maxiter >= 0, "CCSD: negative maxiter");
+        const long long O = o, V = v;
+        In foo(c, f_oo, O * O), fov(c, f_ov, O * V), fvv(c, f_vv, V * V), guess(c, T2_guess, O * O * V * V);
+        IntsDev I;
+        DBuf own[I_COUNT];
+        std::unique_ptr<IntsIn> given;
+        if (so_ints) {// get_integrals, cc.cpp:8-23
+            QCP2_REQUIRE(o + v <= n2, "CCSD: o + v exceeds n2");
+            In so(c, so_ints, ipow4(n2));
+            for (int k = 0; k < I_COUNT; ++k) {
+                own[k] = DBuf(c, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
+                slice_block(c, so, n2, o, v, kIntNames[k], own[k]);
+                I.p[k] = own[k].p;
+            }
+            c.sync();// `so` staging buffer dies here
+        } else {
+            given.reset(new IntsIn(c, ints, o, v, kNeedAll));
+            I = given->dev;
+        }
+        Out t1(c, T1, O * V), t2(c, T2, O * O * V * V);
+        ccsd_dev(c, I, foo, f_ov ? fov.p : nullptr, fvv, guess, o, v, maxiter, conv, t1, t2, energy, iters, e_hist);
+        t1.finish(), t2.finish();
+        if (sliced_out)
+            for (int k = 0; k < I_COUNT; ++k)
+                if (sliced_out[k]) {
+                    const long long n = int_block_size(k, o, v);
+                    QCP2_CUDA(cudaMemcpyAsync(sliced_out[k], I.p[k], (size_t) n * 8,
+                                              c.pointer_mode == QCP2_DEVICE ? cudaMemcpyDeviceToDevice
+                                                                            : cudaMemcpyDeviceToHost,
+                                              c.stream));
+                }
+        c.sync();
+    });
+}
+
+double qcp2_ccsd_last_loop_seconds(const qcp2_ctx *ctx) { return ctx ? ctx->c.ccsd_loop_seconds : 0.0; }
+
+// ---- (T) --------------------------------------------------------------------------
+long long qcp2_ccsd_t_count(int o, int mode) { return t_count(o, mode); }
+
+int qcp2_ccsd_t_select_mode(qcp2_ctx *ctx, const double *T2, const double *oovv, const double *vovv,
+                            const double *ovoo, int o, int v, int *mode) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(T2 && oovv && vovv && ovoo && mode, "(T): null argument");
+        const long long O = o, V = v;
+        In t2(c, T2, O * O * V * V), g(c, oovv, O * O * V * V), w(c, vovv, V * O * V * V), x(c, ovoo, O * V * O * O);
+        *mode = t_select_mode(c, t2, g, w, x, o, v);
+    });
+}
+
+int qcp2_ccsd_t_range(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                      const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
+                      long long first, long long stride, long long max_count, double *e_triples, double *energy) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v && energy, "(T): null argument");
+        const long long O = o, V = v;
+        In t1(c, T1, O * V), t2(c, T2, O * O * V * V), g(c, oovv, O * O * V * V), w(c, vovv, V * O * V * V),
+                x(c, ovoo, O * V * O * O), eo(c, eps_o, O), ev(c, eps_v, V);
+        int m = mode;
+        if (m == QCP2_T_AUTO) m = t_select_mode(c, t2, g, w, x, o, v);
+        std::unique_ptr<TPlan> plan(t_plan_create(c, t1, t2, g, w, x, eo, ev, o, v, m));
+        const long long nt = plan->ntriples;
+        DBuf et;
+        if (e_triples) {
+            et = DBuf(c, (size_t) std::max<long long>(nt, 1));
+            fill_zero(c, et, nt);
+        }
+        t_plan_run(*plan, first, stride, max_count, e_triples ? et.p : nullptr, energy);
+        if (e_triples && nt > 0) {
+            // only the evaluated entries are written back; the rest of e_triples is left untouched
+            std::vector<double> h((size_t) nt);
+            QCP2_CUDA(cudaMemcpyAsync(h.data(), et.p, (size_t) nt * 8, cudaMemcpyDeviceToHost, c.stream));
+            c.sync();
+            long long cnt = first < nt ? (nt - first + stride - 1) / stride : 0;
+            if (max_count >= 0) cnt = std::min(cnt, max_count);
+            for (long long q = 0; q < cnt; ++q) e_triples[first + q * stride] = h[(size_t) (first + q * stride)];
+        }
+        c.sync();
+    });
+}
+
+int qcp2_ccsd_t(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
+                double *energy) {
+    return qcp2_ccsd_t_range(ctx, T1, T2, oovv, vovv, ovoo, eps_o, eps_v, o, v, mode, 0, 1, -1, nullptr, energy);
+}
+
+int qcp2_t_plan_create(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                       const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
+                       qcp2_t_plan **plan) {
+    if (plan) *plan = nullptr;
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(plan && T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v, "(T) plan: null argument");
+        QCP2_REQUIRE(c.pointer_mode == QCP2_DEVICE, "(T) plan: needs QCP2_DEVICE pointer mode (resident inputs)");
+        int m = mode;
+        if (m == QCP2_T_AUTO) m = t_select_mode(c, T2, oovv, vovv, ovoo, o, v);
+        std::unique_ptr<qcp2_t_plan> p(new qcp2_t_plan());
+        p->owner = ctx;
+        p->plan.reset(t_plan_create(c, T1, T2, oovv, vovv, ovoo, eps_o, eps_v, o, v, m));
+        *plan = p.release();
+    });
+}
+
+int qcp2_t_plan_run(qcp2_t_plan *plan, long long first, long long stride, long long max_count,
+                    double *e_triples_dev, double *energy) {
+    if (!plan) return 2;
+    return guarded(plan->owner, [&](Ctx &) {
+        QCP2_REQUIRE(energy, "(T) plan: null energy pointer");
+        t_plan_run(*plan->plan, first, stride, max_count, e_triples_dev, energy);
+    });
+}
+
+int qcp2_t_plan_timings(const qcp2_t_plan *plan, double *gemm_seconds, double *total_seconds,
+                        long long *gemm_launches, long long *all_launches) {
+    if (!plan) return 2;
+    if (gemm_seconds) *gemm_seconds = plan->plan->last_gemm_seconds;
+    if (total_seconds) *total_seconds = plan->plan->last_total_seconds;
+    if (gemm_launches) *gemm_launches = plan->plan->last_gemm_launches;
+    if (all_launches) *all_launches = plan->plan->last_all_launches;
+    return 0;
+}
+
+int qcp2_t_plan_destroy(qcp2_t_plan *plan) {
+    if (!plan) return 0;
+    cudaSetDevice(plan->owner->c.device);
+    delete plan;
+    return 0;
+}
+
+// ---- building blocks ----------------------------------------------------------------
+int qcp2_contract(qcp2_ctx *ctx, double alpha, const double *A, const long long *extA, const char *ia,
+                  const double *B, const long long *extB, const char *ib, double beta, double *C,
+                  const long long *extC, const char *ic) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(A && B && C && ia && ib && ic && extA && extB && extC, "contract: null argument");
+        QCP2_REQUIRE(strlen(ia) <= 8 && strlen(ib) <= 8 && strlen(ic) <= 8, "contract: rank > 8");
+        TView a, b, cc;
+        a.rank = (int) strlen(ia), b.rank = (int) strlen(ib), cc.rank = (int) strlen(ic);
+        for (int k = 0; k < a.rank; ++k) a.ext[k] = extA[k];
+        for (int k = 0; k < b.rank; ++k) b.ext[k] = extB[k];
+        for (int k = 0; k < cc.rank; ++k) cc.ext[k] = extC[k];
+        In ain(c, A, a.size()), bin(c, B, b.size());
+        // C is read when beta != 0
+        DBuf cbuf;
+        double *cp = C;
+        if (c.pointer_mode == QCP2_HOST) {
+            cbuf = DBuf(c, (size_t) std::max<long long>(cc.size(), 1));
+            QCP2_CUDA(cudaMemcpyAsync(cbuf.p, C, (size_t) cc.size() * 8, cudaMemcpyHostToDevice, c.stream));
+            cp = cbuf.p;
+        }
+        a.p = const_cast<double *>(ain.p), b.p = const_cast<double *>(bin.p), cc.p = cp;
+        contract(c, alpha, a, ia, b, ib, beta, cc, ic);
+        if (c.pointer_mode == QCP2_HOST)
+            QCP2_CUDA(cudaMemcpyAsync(C, cp, (size_t) cc.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+int qcp2_dgemm(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A,
+               long long lda, const double *B, long long ldb, double beta, double *C, long long ldc) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0, "dgemm: bad argument");
+        QCP2_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "dgemm: leading dimension too small");
+        const long long na = (long long) (transA ? K : M) * lda, nb = (long long) (transB ? N : K) * ldb,
+                        nc = (long long) M * ldc;
+        In a(c, A, na), b(c, B, nb);
+        DBuf cbuf;
+        double *cp = C;
+        if (c.pointer_mode == QCP2_HOST) {
+            cbuf = DBuf(c, (size_t) std::max<long long>(nc, 1));
+            QCP2_CUDA(cudaMemcpyAsync(cbuf.p, C, (size_t) nc * 8, cudaMemcpyHostToDevice, c.stream));
+            cp = cbuf.p;
+        }
+        GemmArgs g;
+        g.M = M, g.N = N, g.K = K, g.alpha = alpha, g.beta = beta;
+        g.A = a, g.lda = lda, g.B = b, g.ldb = ldb, g.C = cp, g.ldc = ldc;
+        gemm(c, g, !transA, !transB);
+        if (c.pointer_mode == QCP2_HOST) QCP2_CUDA(cudaMemcpyAsync(C, cp, (size_t) nc * 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+    });
+}
+
+int qcp2_synth_t_inputs(qcp2_ctx *ctx, int o, int v, unsigned long long seed, double *T1, double *T2, double *oovv,
+                        double *vovv, double *ovoo, double *eps_o, double *eps_v) {
+    return guarded(ctx, [&](Ctx &c) {
+        synth_t_inputs(c, o, v, seed, T1, T2, oovv, vovv, ovoo, eps_o, eps_v);
+        c.sync();
+    });
+}
+
+}// extern "C"

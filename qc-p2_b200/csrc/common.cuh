@@ -1,0 +1,116 @@
+// common.cuh -- context, error handling and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace qcp2 {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define QCP2_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::qcp2::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + \
+                                __FILE__ + ":" + std::to_string(__LINE__));                         \
+    } while (0)
+
+#define QCP2_REQUIRE(cond, msg)                       \
+    do {                                              \
+        if (!(cond)) throw ::qcp2::Error(std::string(msg)); \
+    } while (0)
+
+// Execution context: one device, one stream, a stream-ordered workspace allocator and a
+// launch counter (bench.py reports it as gpu_launches).
+struct Ctx {
+    int device = 0;
+    int pointer_mode = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    long long launches = 0;
+    std::string last_error;
+    double ccsd_loop_seconds = 0.0;
+
+    double *alloc(size_t n_doubles) {
+        void *p = nullptr;
+        if (n_doubles == 0) n_doubles = 1;
+        QCP2_CUDA(cudaMallocAsync(&p, n_doubles * sizeof(double), stream));
+        return static_cast<double *>(p);
+    }
+    void *alloc_bytes(size_t n) {
+        void *p = nullptr;
+        QCP2_CUDA(cudaMallocAsync(&p, n ? n : 1, stream));
+        return p;
+    }
+    void free(void *p) {
+        if (p) cudaFreeAsync(p, stream);
+    }
+    void sync() { QCP2_CUDA(cudaStreamSynchronize(stream)); }
+    void launched(const char *what) {
+        ++launches;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) throw Error(std::string("kernel launch failed (") + what + "): " + cudaGetErrorString(e));
+    }
+};
+
+// RAII stream-ordered device buffer
+struct DBuf {
+    Ctx *ctx = nullptr;
+    double *p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(Ctx &c, size_t n_) : ctx(&c), p(c.alloc(n_)), n(n_) {}
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    DBuf(DBuf &&o) noexcept : ctx(o.ctx), p(o.p), n(o.n) { o.p = nullptr; }
+    DBuf &operator=(DBuf &&o) noexcept {
+        if (this != &o) {
+            reset();
+            ctx = o.ctx, p = o.p, n = o.n;
+            o.p = nullptr;
+        }
+        return *this;
+    }
+    void reset() {
+        if (p && ctx) ctx->free(p);
+        p = nullptr;
+    }
+    ~DBuf() { reset(); }
+    operator double *() const { return p; }
+};
+
+// Dense row-major tensor view on device memory (rank <= 8).
+struct TView {
+    double *p = nullptr;
+    int rank = 0;
+    long long ext[8] = {1, 1, 1, 1, 1, 1, 1, 1};
+    TView() {}
+    TView(double *ptr, std::initializer_list<long long> e) : p(ptr), rank((int) e.size()) {
+        int k = 0;
+        for (long long x : e) ext[k++] = x;
+    }
+    TView(const double *ptr, std::initializer_list<long long> e) : TView(const_cast<double *>(ptr), e) {}
+    long long size() const {
+        long long n = 1;
+        for (int k = 0; k < rank; ++k) n *= ext[k];
+        return n;
+    }
+};
+
+inline unsigned grid_for(long long n, int block, int sm_count, int per_sm = 16) {
+    long long g = (n + block - 1) / block;
+    long long cap = (long long) sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned) g;
+}
+
+}// namespace qcp2

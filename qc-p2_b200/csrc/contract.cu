@@ -1,0 +1,208 @@
+// contract.cu -- device replacement of btas::contract, the reference's only arithmetic
+// primitive (71 call sites: integrals.cpp:121-129, cc.cpp:194-371, 501-523):
+//     C[ic] = beta*C[ic] + alpha * sum_{labels in A and B only} A[ia]*B[ib]
+// Each call is mapped onto ONE DMMA GEMM.  Operands whose index order already factors into
+// (free block, contracted block) in either order are consumed in place through the GEMM's
+// transposed-operand variants; a leading index shared by C and one operand is peeled off as
+// the GEMM batch dimension; only operands with interleaved index groups are re-laid out
+// (bandwidth-bound permute kernel), and the result is permuted back only if C's own index
+// order interleaves the two free groups.
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+#include "contract.cuh"
+#include "dgemm.cuh"
+#include "tensor_ops.cuh"
+
+namespace qcp2 {
+
+namespace {
+
+struct Spec {
+    std::string a, b, c;               // label strings (after peeling)
+    long long ea[8], eb[8], ec[8];     // extents
+};
+
+long long ext_of(const std::string &s, const long long *e, char l) {
+    const size_t p = s.find(l);
+    return e[p];
+}
+long long prod(const std::string &labels, const std::string &s, const long long *e) {
+    long long n = 1;
+    for (char l : labels) n *= ext_of(s, e, l);
+    return n;
+}
+long long total(const std::string &s, const long long *e) {
+    long long n = 1;
+    for (size_t k = 0; k < s.size(); ++k) n *= e[k];
+    return n;
+}
+
+struct Plan {
+    std::string M, N, K;// canonical label orders
+    bool a_direct = false, a_kc = true;
+    bool b_direct = false, b_nc = true;
+    bool c_direct = false, c_swapped = false;
+    double cost = 0.0;
+};
+
+Plan make_plan(const Spec &s, const std::string &M, const std::string &N, const std::string &K) {
+    Plan p;
+    p.M = M, p.N = N, p.K = K;
+    if (s.a == M + K) p.a_direct = true, p.a_kc = true;
+    else if (s.a == K + M) p.a_direct = true, p.a_kc = false;
+    if (s.b == K + N) p.b_direct = true, p.b_nc = true;
+    else if (s.b == N + K) p.b_direct = true, p.b_nc = false;
+    if (s.c == M + N) p.c_direct = true, p.c_swapped = false;
+    else if (s.c == N + M) p.c_direct = true, p.c_swapped = true;
+    p.cost = (p.a_direct ? 0.0 : 2.0 * (double) total(s.a, s.ea)) + (p.b_direct ? 0.0 : 2.0 * (double) total(s.b, s.eb)) +
+             (p.c_direct ? 0.0 : 3.0 * (double) total(s.c, s.ec));
+    return p;
+}
+
+Plan best_plan(const Spec &s) {
+    std::string M, N, Ka, Kb;
+    for (char l : s.c) {
+        const bool ina = s.a.find(l) != std::string::npos, inb = s.b.find(l) != std::string::npos;
+        QCP2_REQUIRE(ina != inb, "contract: every output label must occur in exactly one operand");
+        (ina ? M : N).push_back(l);
+    }
+    for (char l : s.a)
+        if (s.c.find(l) == std::string::npos) {
+            QCP2_REQUIRE(s.b.find(l) != std::string::npos, "contract: dangling label in A");
+            Ka.push_back(l);
+        }
+    for (char l : s.b)
+        if (s.c.find(l) == std::string::npos) {
+            QCP2_REQUIRE(s.a.find(l) != std::string::npos, "contract: dangling label in B");
+            Kb.push_back(l);
+        }
+    QCP2_REQUIRE(Ka.size() == Kb.size(), "contract: contracted label sets differ");
+    for (char l : Ka) QCP2_REQUIRE(ext_of(s.a, s.ea, l) == ext_of(s.b, s.eb, l), "contract: contracted extents differ");
+    for (char l : M) QCP2_REQUIRE(ext_of(s.a, s.ea, l) == ext_of(s.c, s.ec, l), "contract: free extents differ (A)");
+    for (char l : N) QCP2_REQUIRE(ext_of(s.b, s.eb, l) == ext_of(s.c, s.ec, l), "contract: free extents differ (B)");
+    Plan pa = make_plan(s, M, N, Ka);
+    if (Ka == Kb) return pa;
+    Plan pb = make_plan(s, M, N, Kb);
+    return pb.cost < pa.cost ? pb : pa;
+}
+
+// re-lay `src` (labels `from`) out as a dense tensor with labels `to`
+void relayout(Ctx &ctx, double *dst, const double *src, const std::string &from, const long long *efrom,
+              const std::string &to, double alpha, double beta) {
+    long long istr_from[8];
+    long long s = 1;
+    for (int k = (int) from.size() - 1; k >= 0; --k) istr_from[k] = s, s *= efrom[k];
+    long long oext[8], istr[8];
+    for (size_t k = 0; k < to.size(); ++k) {
+        const size_t p = from.find(to[k]);
+        oext[k] = efrom[p], istr[k] = istr_from[p];
+    }
+    permute_axpby(ctx, dst, src, (int) to.size(), oext, istr, alpha, beta);
+}
+
+void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, double *C, const Spec &s,
+         const Plan &p, int batch, long long sA, long long sB, long long sC) {
+    const long long M = prod(p.M, s.c, s.ec), N = prod(p.N, s.c, s.ec), K = prod(p.K, s.a, s.ea);
+    QCP2_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "contract: GEMM extent exceeds 2^31");
+    DBuf ta, tb, tc;
+    const double *Ag = A, *Bg = B;
+    long long sAg = sA, sBg = sB;
+    bool a_kc = p.a_kc, b_nc = p.b_nc;
+    if (!p.a_direct) {// -> [M][K]
+        const long long n = total(s.a, s.ea);
+        ta = DBuf(ctx, (size_t) (n * (sA ? batch : 1)));
+        for (int z = 0; z < (sA ? batch : 1); ++z) relayout(ctx, ta.p + z * n, A + z * sA, s.a, s.ea, p.M + p.K, 1.0, 0.0);
+        Ag = ta.p, a_kc = true, sAg = sA ? n : 0;
+    }
+    if (!p.b_direct) {// -> [K][N]
+        const long long n = total(s.b, s.eb);
+        tb = DBuf(ctx, (size_t) (n * (sB ? batch : 1)));
+        for (int z = 0; z < (sB ? batch : 1); ++z) relayout(ctx, tb.p + z * n, B + z * sB, s.b, s.eb, p.K + p.N, 1.0, 0.0);
+        Bg = tb.p, b_nc = true, sBg = sB ? n : 0;
+    }
+    GemmArgs g;
+    g.batch = batch;
+    g.alpha = alpha;
+    double *Cg = C;
+    long long sCg = sC;
+    bool swapped = p.c_direct && p.c_swapped;
+    if (!p.c_direct) {
+        const long long n = total(s.c, s.ec);
+        tc = DBuf(ctx, (size_t) (n * batch));
+        Cg = tc.p, sCg = n, g.beta = 0.0;
+    } else {
+        g.beta = beta;
+    }
+    if (!swapped) {
+        g.M = (int) M, g.N = (int) N, g.K = (int) K;
+        g.A = Ag, g.lda = a_kc ? K : M, g.strideA = sAg;
+        g.B = Bg, g.ldb = b_nc ? N : K, g.strideB = sBg;
+        g.C = Cg, g.ldc = N, g.strideC = sCg;
+        gemm(ctx, g, a_kc, b_nc);
+    } else {// C^T[N][M] = B^T[N][K] . A^T[K][M]
+        g.M = (int) N, g.N = (int) M, g.K = (int) K;
+        g.A = Bg, g.lda = b_nc ? N : K, g.strideA = sBg;
+        g.B = Ag, g.ldb = a_kc ? K : M, g.strideB = sAg;
+        g.C = Cg, g.ldc = M, g.strideC = sCg;
+        gemm(ctx, g, /*a_kc=*/!b_nc, /*b_nc=*/!a_kc);
+    }
+    if (!p.c_direct) {
+        const std::string mn = p.M + p.N;
+        long long emn[8];
+        for (size_t k = 0; k < mn.size(); ++k) emn[k] = ext_of(s.c, s.ec, mn[k]);
+        const long long n = total(s.c, s.ec);
+        for (int z = 0; z < batch; ++z) relayout(ctx, C + z * sC, tc.p + z * n, mn, emn, s.c, 1.0, beta);
+    }
+}
+
+}// namespace
+
+void contract(Ctx &ctx, double alpha, const TView &A, const char *ia, const TView &B, const char *ib, double beta,
+              const TView &C, const char *ic) {
+    Spec s;
+    s.a = ia, s.b = ib, s.c = ic;
+    QCP2_REQUIRE((int) s.a.size() == A.rank && (int) s.b.size() == B.rank && (int) s.c.size() == C.rank,
+                 "contract: label count does not match tensor rank");
+    for (int k = 0; k < A.rank; ++k) s.ea[k] = A.ext[k];
+    for (int k = 0; k < B.rank; ++k) s.eb[k] = B.ext[k];
+    for (int k = 0; k < C.rank; ++k) s.ec[k] = C.ext[k];
+    if (C.size() == 0) return;
+    Plan p0 = best_plan(s);
+    // try peeling the leading label of C as a batch dimension
+    bool peel = false;
+    Spec sp = s;
+    Plan pp;
+    long long sA = 0, sB = 0, sC = 0;
+    int batch = 1;
+    if (p0.cost > 0.0 && s.c.size() >= 2) {
+        const char l = s.c[0];
+        const bool lead_a = !s.a.empty() && s.a[0] == l, lead_b = !s.b.empty() && s.b[0] == l;
+        if ((lead_a || lead_b) && s.ec[0] <= 65535) {
+            sp.c = s.c.substr(1);
+            for (size_t k = 0; k + 1 < s.c.size(); ++k) sp.ec[k] = s.ec[k + 1];
+            if (lead_a) {
+                sp.a = s.a.substr(1);
+                for (size_t k = 0; k + 1 < s.a.size(); ++k) sp.ea[k] = s.ea[k + 1];
+                sA = total(sp.a, sp.ea);
+            } else {
+                sp.b = s.b.substr(1);
+                for (size_t k = 0; k + 1 < s.b.size(); ++k) sp.eb[k] = s.eb[k + 1];
+                sB = total(sp.b, sp.eb);
+            }
+            sC = total(sp.c, sp.ec);
+            batch = (int) s.ec[0];
+            pp = best_plan(sp);
+            // cost of the peeled plan counts every batch member of the batched tensors
+            const double scaled = (pp.a_direct ? 0.0 : 2.0 * (double) total(sp.a, sp.ea) * (sA ? batch : 1)) +
+                                  (pp.b_direct ? 0.0 : 2.0 * (double) total(sp.b, sp.eb) * (sB ? batch : 1)) +
+                                  (pp.c_direct ? 0.0 : 3.0 * (double) total(sp.c, sp.ec) * batch);
+            if (scaled < p0.cost) peel = true;
+        }
+    }
+    if (peel) run(ctx, alpha, A.p, B.p, beta, C.p, sp, pp, batch, sA, sB, sC);
+    else run(ctx, alpha, A.p, B.p, beta, C.p, s, p0, 1, 0, 0, 0);
+}
+
+}// namespace qcp2

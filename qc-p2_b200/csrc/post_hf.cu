@@ -1,0 +1,266 @@
+// post_hf.cu -- AO->MO transform, MP2 and the spin-orbital CCSD iteration, device resident.
+//
+// Each reference contraction (a btas::contract call) is one call of qcp2::contract with the
+// same index labels as the cited reference line, so the term list can be audited against
+// cc.cpp line by line; the elementwise pieces are the kernels of tensor_ops.cu.
+#include <cmath>
+
+#include "contract.cuh"
+#include "dgemm.cuh"
+#include "post_hf.cuh"
+#include "tensor_ops.cuh"
+
+namespace qcp2 {
+
+const char *const kIntNames[I_COUNT] = {"oooo", "ovoo", "oovo", "ooov", "ovov", "ovvo",
+                                        "oovv", "vovv", "ovvv", "vvvo", "vvvv"};
+
+long long int_block_size(int k, int o, int v) {
+    long long n = 1;
+    for (int d = 0; d < 4; ++d) n *= (kIntNames[k][d] == 'o') ? o : v;
+    return n;
+}
+long long inter_block_size(int k, int o, int v) {
+    const long long O = o, V = v;
+    switch (k) {
+        case X_FAE: return V * V;
+        case X_FMI: return O * O;
+        case X_FME: return O * V;
+        case X_WMNIJ: return O * O * O * O;
+        case X_WMBEJ: return O * V * V * O;
+        default: return V * V * V * V;
+    }
+}
+
+static TView int_view(const IntsDev &I, int k, int o, int v) {
+    TView t;
+    t.p = const_cast<double *>(I.p[k]);
+    t.rank = 4;
+    for (int d = 0; d < 4; ++d) t.ext[d] = (kIntNames[k][d] == 'o') ? o : v;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------
+// integrals.cpp:95-134 -- four quarter transformations, 2 n^5 flop each, as four GEMM
+// launches (two of them batched) without any re-layout:
+//   X1[(pqr), l]    = sum_s ao[(pqr), s]   C1[s, l]                      (:121)
+//   X2[(pq)][k][l]  = sum_r C1[r, k]       X1[(pq)][r][l]   batch n^2    (:123)
+//   X3[p][j][(kl)]  = sum_q C2[q, j]       X2[p][q][(kl)]   batch n      (:126)
+//   out[i][(jkl)]   = sum_p C2[p, i]       X3[p][(jkl)]                  (:129)
+// ---------------------------------------------------------------------------------
+void transform_ao_mo_dev(Ctx &ctx, const double *ao, const double *C1, const double *C2, int n, double *out) {
+    QCP2_REQUIRE(n >= 1 && n <= 255, "transform_ao_mo: n out of range (1..255)");
+    const long long n2 = (long long) n * n, n3 = n2 * n, n4 = n3 * n;
+    DBuf x1(ctx, (size_t) n4), x2(ctx, (size_t) n4);
+    GemmArgs g;
+    g.M = (int) n3, g.N = n, g.K = n;
+    g.A = ao, g.lda = n, g.B = C1, g.ldb = n, g.C = x1, g.ldc = n;
+    gemm(ctx, g, true, true);
+
+    g = GemmArgs();
+    g.M = n, g.N = n, g.K = n, g.batch = (int) n2;
+    g.A = C1, g.lda = n, g.strideA = 0;      // [K=r][M=k]
+    g.B = x1, g.ldb = n, g.strideB = n2;     // [K=r][N=l]
+    g.C = x2, g.ldc = n, g.strideC = n2;
+    gemm(ctx, g, false, true);
+
+    g = GemmArgs();
+    g.M = n, g.N = (int) n2, g.K = n, g.batch = n;
+    g.A = C2, g.lda = n, g.strideA = 0;      // [K=q][M=j]
+    g.B = x2, g.ldb = n2, g.strideB = n3;    // [K=q][N=(kl)]
+    g.C = x1, g.ldc = n2, g.strideC = n3;    // x1 reused as X3
+    gemm(ctx, g, false, true);
+
+    g = GemmArgs();
+    g.M = n, g.N = (int) n3, g.K = n;
+    g.A = C2, g.lda = n;                     // [K=p][M=i]
+    g.B = x1, g.ldb = n3;                    // [K=p][N=(jkl)]
+    g.C = out, g.ldc = n3;
+    gemm(ctx, g, false, true);
+}
+
+// mp2.cpp:45-86 from the AO integrals on.
+void mp2_dev(Ctx &ctx, const double *ao, const double *Ca, const double *Cb, const double *ea, const double *eb, int n,
+             int o, int v, bool uhf, double *so_ints, double *T, double *e_host) {
+    const long long n4 = (long long) n * n * n * n, n2 = 2LL * n;
+    QCP2_REQUIRE(o >= 0 && v >= 0 && o + v == n2, "MP2: o + v must equal 2n");
+    DBuf so_own;
+    if (!so_ints) so_own = DBuf(ctx, (size_t) (16 * n4)), so_ints = so_own;
+    {
+        DBuf aa(ctx, (size_t) n4);
+        transform_ao_mo_dev(ctx, ao, Ca, Ca, n, aa);// mp2.cpp:55 / :71
+        if (!uhf) {
+            to_so(ctx, aa, aa, aa, n, so_ints);// :58
+        } else {
+            DBuf bb(ctx, (size_t) n4), ab(ctx, (size_t) n4);
+            transform_ao_mo_dev(ctx, ao, Cb, Cb, n, bb);// :72
+            transform_ao_mo_dev(ctx, ao, Ca, Cb, n, ab);// :73 (Coeff1 = Ca -> k,l ; Coeff2 = Cb -> i,j)
+            to_so(ctx, aa, bb, ab, n, so_ints);         // :75
+        }
+    }
+    DBuf F(ctx, (size_t) (n2 * n2)), oovv(ctx, (size_t) ((long long) o * o * v * v)),
+            den(ctx, (size_t) ((long long) o * o * v * v)), e(ctx, 1);
+    make_so_moes(ctx, ea, uhf ? eb : ea, n, F);
+    slice_block(ctx, so_ints, (int) n2, o, v, "oovv", oovv);
+    make_denom(ctx, F, (int) n2, o, v, den);
+    mp2_amplitudes_energy(ctx, oovv, den, (long long) o * o * v * v, T, e);
+    QCP2_CUDA(cudaMemcpyAsync(e_host, e.p, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+}
+
+// ---------------------------------------------------------------------------------
+// cc.cpp:175-255 -- Stanton eqs. 3-8
+// ---------------------------------------------------------------------------------
+void update_intermediates_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const double *foo,
+                              const double *fov, const double *fvv, int o, int v, const InterDev &X) {
+    const long long O = o, V = v, o2v2 = O * O * V * V;
+    const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
+    const TView oooo = int_view(I, I_OOOO, o, v), ooov = int_view(I, I_OOOV, o, v), oovo = int_view(I, I_OOVO, o, v),
+                oovv = int_view(I, I_OOVV, o, v), vovv = int_view(I, I_VOVV, o, v), ovvv = int_view(I, I_OVVV, o, v);
+    DBuf taub(ctx, (size_t) o2v2), tau(ctx, (size_t) o2v2), tt(ctx, (size_t) o2v2);
+    make_tau(ctx, Ts, Td, o, v, true, taub);
+    make_tau(ctx, Ts, Td, o, v, false, tau);
+    multiply_Ts(ctx, Ts, o, v, tt);
+    const TView vtaub(taub.p, {O, O, V, V}), vtau(tau.p, {O, O, V, V}), vtt(tt.p, {O, V, O, V});
+
+    const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
+    const TView Wmnij(X.p[X_WMNIJ], {O, O, O, O}), Wmbej(X.p[X_WMBEJ], {O, V, V, O}), Wabef(X.p[X_WABEF], {V, V, V, V});
+
+    fill_zero(ctx, Fae.p, V * V);
+    if (fov) contract(ctx, -0.5, TView(fov, {O, V}), "me", ts, "ma", 1.0, Fae, "ae");// :194
+    contract(ctx, 1.0, ts, "mf", ovvv, "mafe", 1.0, Fae, "ae");                      // :195
+    contract(ctx, -0.5, vtaub, "mnaf", oovv, "mnef", 1.0, Fae, "ae");                // :196
+    add_offdiag(ctx, Fae.p, fvv, v);                                                // :198-202
+
+    fill_zero(ctx, Fmi.p, O * O);
+    if (fov) contract(ctx, 0.5, ts, "ie", TView(fov, {O, V}), "me", 1.0, Fmi, "mi"); // :207
+    contract(ctx, 1.0, ts, "ne", ooov, "mnie", 1.0, Fmi, "mi");                      // :208
+    contract(ctx, 0.5, vtaub, "inef", oovv, "mnef", 1.0, Fmi, "mi");                 // :209
+    add_offdiag(ctx, Fmi.p, foo, o);                                                // :212-216
+
+    contract(ctx, 1.0, ts, "nf", oovv, "mnef", 0.0, Fme, "me");                      // :220
+    if (fov) axpby(ctx, Fme.p, fov, 1.0, 1.0, O * V);                                // :221-225
+
+    contract(ctx, 1.0, ts, "je", ooov, "mnie", 0.0, Wmnij, "mnij");                  // :229
+    contract(ctx, -1.0, ts, "ie", ooov, "mnje", 1.0, Wmnij, "mnij");                 // :230
+    contract(ctx, 0.25, vtau, "ijef", oovv, "mnef", 1.0, Wmnij, "mnij");             // :231
+    axpby(ctx, Wmnij.p, oooo.p, 1.0, 1.0, O * O * O * O);                            // :232
+
+    contract(ctx, -1.0, ts, "mb", vovv, "amef", 0.0, Wabef, "abef");                 // :237
+    contract(ctx, 1.0, ts, "ma", vovv, "bmef", 1.0, Wabef, "abef");                  // :238
+    contract(ctx, 0.25, vtau, "mnab", oovv, "mnef", 1.0, Wabef, "abef");             // :239
+    axpby(ctx, Wabef.p, I.p[I_VVVV], 1.0, 1.0, V * V * V * V);                       // :240
+
+    contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 0.0, Wmbej, "mbej");                  // :245
+    contract(ctx, -1.0, ts, "nb", oovo, "mnej", 1.0, Wmbej, "mbej");                 // :246
+    contract(ctx, -0.5, td, "jnfb", oovv, "mnef", 1.0, Wmbej, "mbej");               // :247
+    contract(ctx, -1.0, vtt, "jfnb", oovv, "mnef", 1.0, Wmbej, "mbej");              // :249
+    axpby(ctx, Wmbej.p, I.p[I_OVVO], 1.0, 1.0, O * V * V * O);                       // :250
+}
+
+// cc.cpp:257-292 -- Stanton eq. 1
+void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
+                 const double *fov, const double *fvv, int o, int v, double *T1_new) {
+    const long long O = o, V = v;
+    const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
+    DBuf r(ctx, (size_t) (O * V));
+    const TView R(r.p, {O, V});
+    contract(ctx, 1.0, ts, "ie", TView(X.p[X_FAE], {V, V}), "ae", 0.0, R, "ia");       // :272
+    contract(ctx, -1.0, ts, "ma", TView(X.p[X_FMI], {O, O}), "mi", 1.0, R, "ia");      // :273
+    contract(ctx, 1.0, td, "imae", TView(X.p[X_FME], {O, V}), "me", 1.0, R, "ia");     // :274
+    contract(ctx, -1.0, ts, "nf", int_view(I, I_OVOV, o, v), "naif", 1.0, R, "ia");    // :275
+    contract(ctx, -0.5, td, "imef", int_view(I, I_OVVV, o, v), "maef", 1.0, R, "ia");  // :276
+    contract(ctx, -0.5, td, "mnae", int_view(I, I_OOVO, o, v), "nmei", 1.0, R, "ia");  // :277
+    if (fov) axpby(ctx, r.p, fov, 1.0, 1.0, O * V);                                    // :280
+    divide_D_ia(ctx, r, foo, fvv, o, v, T1_new);                                       // :283-288
+}
+
+// cc.cpp:294-387 -- Stanton eq. 2
+void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
+                 const double *fvv, int o, int v, double *T2_new) {
+    const long long O = o, V = v, o2v2 = O * O * V * V;
+    const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
+    const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
+    const TView Wmnij(X.p[X_WMNIJ], {O, O, O, O}), Wmbej(X.p[X_WMBEJ], {O, V, V, O}), Wabef(X.p[X_WABEF], {V, V, V, V});
+    const TView ovov = int_view(I, I_OVOV, o, v), vvvo = int_view(I, I_VVVO, o, v), ovoo = int_view(I, I_OVOO, o, v);
+    DBuf r(ctx, (size_t) o2v2), tau(ctx, (size_t) o2v2), tt(ctx, (size_t) o2v2), d1(ctx, (size_t) (V * V)),
+            d2(ctx, (size_t) (O * O));
+    const TView R(r.p, {O, O, V, V}), D1(d1.p, {V, V}), D2(d2.p, {O, O});
+    make_tau(ctx, Ts, Td, o, v, false, tau);
+    multiply_Ts(ctx, Ts, o, v, tt);
+    const TView vtau(tau.p, {O, O, V, V}), vtt(tt.p, {O, V, O, V});
+
+    axpby(ctx, r.p, I.p[I_OOVV], 1.0, 0.0, o2v2);                       // :312
+    contract(ctx, 1.0, td, "ijae", Fae, "be", 1.0, R, "ijab");          // :316
+    contract(ctx, -1.0, td, "ijbe", Fae, "ae", 1.0, R, "ijab");         // :317
+    contract(ctx, 1.0, ts, "mb", Fme, "me", 0.0, D1, "be");             // :322
+    contract(ctx, -0.5, td, "ijae", D1, "be", 1.0, R, "ijab");          // :324
+    contract(ctx, 1.0, ts, "ma", Fme, "me", 0.0, D1, "ae");             // :326-327
+    contract(ctx, 0.5, td, "ijbe", D1, "ae", 1.0, R, "ijab");           // :328
+    contract(ctx, -1.0, td, "imab", Fmi, "mj", 1.0, R, "ijab");         // :333
+    contract(ctx, 1.0, td, "jmab", Fmi, "mi", 1.0, R, "ijab");          // :334
+    contract(ctx, 1.0, ts, "je", Fme, "me", 0.0, D2, "jm");             // :339
+    contract(ctx, -0.5, td, "imab", D2, "jm", 1.0, R, "ijab");          // :340
+    contract(ctx, 1.0, ts, "ie", Fme, "me", 0.0, D2, "im");             // :341-342
+    contract(ctx, 0.5, td, "jmab", D2, "im", 1.0, R, "ijab");           // :343
+    contract(ctx, 0.5, vtau, "mnab", Wmnij, "mnij", 1.0, R, "ijab");    // :346
+    contract(ctx, 0.5, vtau, "ijef", Wabef, "abef", 1.0, R, "ijab");    // :348  particle-particle ladder
+    contract(ctx, 1.0, td, "imae", Wmbej, "mbej", 1.0, R, "ijab");      // :354  ring terms
+    contract(ctx, -1.0, td, "jmae", Wmbej, "mbei", 1.0, R, "ijab");     // :355
+    contract(ctx, -1.0, td, "imbe", Wmbej, "maej", 1.0, R, "ijab");     // :356
+    contract(ctx, 1.0, td, "jmbe", Wmbej, "maei", 1.0, R, "ijab");      // :357
+    contract(ctx, 1.0, vtt, "iema", ovov, "mbje", 1.0, R, "ijab");      // :360
+    contract(ctx, -1.0, vtt, "jema", ovov, "mbie", 1.0, R, "ijab");     // :361
+    contract(ctx, -1.0, vtt, "iemb", ovov, "maje", 1.0, R, "ijab");     // :362
+    contract(ctx, 1.0, vtt, "jemb", ovov, "maie", 1.0, R, "ijab");      // :363
+    contract(ctx, 1.0, ts, "ie", vvvo, "abej", 1.0, R, "ijab");         // :366
+    contract(ctx, -1.0, ts, "je", vvvo, "abei", 1.0, R, "ijab");        // :367
+    contract(ctx, -1.0, ts, "ma", ovoo, "mbij", 1.0, R, "ijab");        // :370
+    contract(ctx, 1.0, ts, "mb", ovoo, "maij", 1.0, R, "ijab");         // :371
+    divide_D_ijab(ctx, r, foo, fvv, o, v, T2_new);                      // :374-383
+}
+
+// cc.cpp:409-451.  Amplitudes, integrals and intermediates never leave the device; the
+// host sees one double per iteration (the energy that decides convergence).
+void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,
+              const double *T2_guess, int o, int v, int maxiter, double conv, double *T1, double *T2, double *e_host,
+              int *iters_host, double *e_hist_host) {
+    const long long O = o, V = v, o2v2 = O * O * V * V;
+    DBuf xbuf[X_COUNT];
+    InterDev X;
+    for (int k = 0; k < X_COUNT; ++k) xbuf[k] = DBuf(ctx, (size_t) inter_block_size(k, o, v)), X.p[k] = xbuf[k].p;
+    DBuf t1n(ctx, (size_t) (O * V)), t2n(ctx, (size_t) o2v2), e_dev(ctx, 1);
+    fill_zero(ctx, T1, O * V);                                                             // :417-419
+    QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
+    cudaEvent_t ev0, ev1;
+    QCP2_CUDA(cudaEventCreate(&ev0));
+    QCP2_CUDA(cudaEventCreate(&ev1));
+    QCP2_CUDA(cudaEventRecord(ev0, ctx.stream));
+    double e_last = 0.0, e = 0.0;
+    int it = 0;
+    for (; it < maxiter; ++it) {
+        ccsd_energy(ctx, T1, T2, I.p[I_OOVV], fov, o, v, e_dev);                           // :432
+        QCP2_CUDA(cudaMemcpyAsync(&e, e_dev.p, 8, cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        const double de = e - e_last;
+        e_last = e;
+        if (e_hist_host) e_hist_host[it] = e;
+        if (std::fabs(de) < conv) break;                                                   // :438 (fabs)
+        update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
+        make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, o, v, t1n);                          // :445
+        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, o, v, t2n);                              // :446: new T1, old T2, old X
+        QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    }
+    QCP2_CUDA(cudaEventRecord(ev1, ctx.stream));
+    QCP2_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    ctx.ccsd_loop_seconds = ms * 1e-3;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    *e_host = e;
+    if (iters_host) *iters_host = it;
+}
+
+}// namespace qcp2

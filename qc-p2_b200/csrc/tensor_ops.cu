@@ -1,0 +1,540 @@
+// tensor_ops.cu -- bandwidth-bound kernels of the post-HF path (see tensor_ops.cuh).
+// Every kernel is a coalesced grid-stride sweep; reductions are two-stage with a fixed
+// grid so the summation order (and therefore the energy bits) is reproducible run to run.
+#include <algorithm>
+#include <cstring>
+
+#include "tensor_ops.cuh"
+
+namespace qcp2 {
+
+static constexpr int kBlock = 256;
+static constexpr int kRedBlocks = 592;// 4 x 148: fixed, so reductions are deterministic
+
+// ---------------------------------------------------------------------------------
+// permutation
+// ---------------------------------------------------------------------------------
+struct PermArgs {
+    int rank;
+    long long ext[8];
+    long long istr[8];
+    long long n;
+};
+
+__global__ void permute_generic_kernel(double *__restrict__ out, const double *__restrict__ in, PermArgs a,
+                                       double alpha, double beta) {
+    for (long long lin = (long long) blockIdx.x * blockDim.x + threadIdx.x; lin < a.n;
+         lin += (long long) gridDim.x * blockDim.x) {
+        long long r = lin, off = 0;
+#pragma unroll 1
+        for (int d = a.rank - 1; d >= 0; --d) {
+            const long long e = a.ext[d];
+            const long long q = r / e;
+            off += (r - q * e) * a.istr[d];
+            r = q;
+        }
+        const double val = alpha * in[off];
+        out[lin] = (beta == 0.0) ? val : val + beta * out[lin];
+    }
+}
+
+// tiled transpose between the input-contiguous output dim `di` and the last output dim
+struct PermTileArgs {
+    int rank;          // rank of the "rest" dims
+    long long ext[8];  // rest extents
+    long long istr[8]; // rest input strides
+    long long ostr[8]; // rest output strides
+    long long ext_i, ext_o;     // extents of di and of the last dim
+    long long istr_o, ostr_i;   // input stride of the last dim; output stride of di
+    long long tiles_i, tiles_o, nrest;
+};
+
+__global__ void permute_tiled_kernel(double *__restrict__ out, const double *__restrict__ in, PermTileArgs a,
+                                     double alpha, double beta) {
+    __shared__ double tile[32][33];
+    const long long ntiles = a.tiles_i * a.tiles_o * a.nrest;
+    for (long long b = blockIdx.x; b < ntiles; b += gridDim.x) {
+        long long r = b;
+        const long long to = r % a.tiles_o;
+        r /= a.tiles_o;
+        const long long ti = r % a.tiles_i;
+        r /= a.tiles_i;
+        long long ibase = 0, obase = 0;
+#pragma unroll 1
+        for (int d = a.rank - 1; d >= 0; --d) {
+            const long long e = a.ext[d];
+            const long long q = r / e;
+            const long long x = r - q * e;
+            ibase += x * a.istr[d], obase += x * a.ostr[d];
+            r = q;
+        }
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;// 32 x 8
+        {
+            const long long ii = ti * 32 + tx;
+#pragma unroll
+            for (int yy = 0; yy < 32; yy += 8) {
+                const long long oo = to * 32 + yy + ty;
+                if (ii < a.ext_i && oo < a.ext_o) tile[yy + ty][tx] = in[ibase + ii + oo * a.istr_o];
+            }
+        }
+        __syncthreads();
+        {
+            const long long oo = to * 32 + tx;
+#pragma unroll
+            for (int yy = 0; yy < 32; yy += 8) {
+                const long long ii = ti * 32 + yy + ty;
+                if (ii < a.ext_i && oo < a.ext_o) {
+                    double *dst = out + obase + ii * a.ostr_i + oo;
+                    const double val = alpha * tile[tx][yy + ty];
+                    *dst = (beta == 0.0) ? val : val + beta * (*dst);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void permute_axpby(Ctx &ctx, double *out, const double *in, int rank, const long long *out_ext,
+                   const long long *in_stride, double alpha, double beta) {
+    QCP2_REQUIRE(rank >= 1 && rank <= 8, "permute: rank out of range");
+    // drop unit dims, merge neighbours that are contiguous in the input as well
+    long long ext[8], istr[8];
+    int r = 0;
+    for (int d = 0; d < rank; ++d) {
+        if (out_ext[d] == 1) continue;
+        if (r > 0 && istr[r - 1] == in_stride[d] * out_ext[d]) {
+            ext[r - 1] *= out_ext[d];
+            istr[r - 1] = in_stride[d];
+        } else {
+            ext[r] = out_ext[d], istr[r] = in_stride[d], ++r;
+        }
+    }
+    long long n = 1;
+    for (int d = 0; d < rank; ++d) n *= out_ext[d];
+    if (n == 0) return;
+    if (r == 0) ext[0] = 1, istr[0] = 1, r = 1;
+    int di = -1;
+    for (int d = 0; d < r; ++d)
+        if (istr[d] == 1) di = d;
+    if (di >= 0 && di != r - 1 && ext[di] >= 8 && ext[r - 1] >= 8) {
+        PermTileArgs a{};
+        long long ostr[8];
+        ostr[r - 1] = 1;
+        for (int d = r - 2; d >= 0; --d) ostr[d] = ostr[d + 1] * ext[d + 1];
+        a.rank = 0;
+        a.nrest = 1;
+        for (int d = 0; d < r - 1; ++d) {
+            if (d == di) continue;
+            a.ext[a.rank] = ext[d], a.istr[a.rank] = istr[d], a.ostr[a.rank] = ostr[d];
+            a.nrest *= ext[d];
+            ++a.rank;
+        }
+        a.ext_i = ext[di], a.ext_o = ext[r - 1];
+        a.istr_o = istr[r - 1], a.ostr_i = ostr[di];
+        a.tiles_i = (a.ext_i + 31) / 32, a.tiles_o = (a.ext_o + 31) / 32;
+        const long long ntiles = a.tiles_i * a.tiles_o * a.nrest;
+        const unsigned grid = (unsigned) std::min<long long>(ntiles, (long long) ctx.sm_count * 32);
+        permute_tiled_kernel<<<grid, 256, 0, ctx.stream>>>(out, in, a, alpha, beta);
+        ctx.launched("permute_tiled");
+        return;
+    }
+    PermArgs a{};
+    a.rank = r, a.n = n;
+    for (int d = 0; d < r; ++d) a.ext[d] = ext[d], a.istr[d] = istr[d];
+    permute_generic_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(out, in, a, alpha, beta);
+    ctx.launched("permute_generic");
+}
+
+// ---------------------------------------------------------------------------------
+// elementwise
+// ---------------------------------------------------------------------------------
+#define GRID_STRIDE(lin, n) \
+    for (long long lin = (long long) blockIdx.x * blockDim.x + threadIdx.x; lin < (n); lin += (long long) gridDim.x * blockDim.x)
+
+__global__ void axpby_kernel(double *__restrict__ out, const double *__restrict__ x, double alpha, double beta,
+                             long long n) {
+    GRID_STRIDE(i, n) out[i] = (beta == 0.0) ? alpha * x[i] : alpha * x[i] + beta * out[i];
+}
+void axpby(Ctx &ctx, double *out, const double *x, double alpha, double beta, long long n) {
+    if (n <= 0) return;
+    axpby_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(out, x, alpha, beta, n);
+    ctx.launched("axpby");
+}
+void fill_zero(Ctx &ctx, double *p, long long n) {
+    if (n > 0) QCP2_CUDA(cudaMemsetAsync(p, 0, (size_t) n * sizeof(double), ctx.stream));
+}
+
+// integrals.cpp:136-167 as a gather: one thread per <ij||kl>, l fastest.
+__global__ void to_so_kernel(const double *__restrict__ aa, const double *__restrict__ bb,
+                             const double *__restrict__ ab, int n, double *__restrict__ so) {
+    const long long n2 = 2LL * n, total = n2 * n2 * n2 * n2;
+    GRID_STRIDE(lin, total) {
+        long long r = lin;
+        const int l = (int) (r % n2);
+        r /= n2;
+        const int k = (int) (r % n2);
+        r /= n2;
+        const int j = (int) (r % n2);
+        const int i = (int) (r / n2);
+        const int si = i & 1, sj = j & 1, sk = k & 1, sl = l & 1;
+        const long long I = i >> 1, J = j >> 1, K = k >> 1, L = l >> 1;
+        const long long ikjl = ((I * n + K) * n + J) * n + L, jkil = ((J * n + K) * n + I) * n + L;
+        double val = 0.0;
+        if (si == sk && sj == sl) {
+            if (si == sj) {
+                const double *m = si ? bb : aa;
+                val = m[ikjl] - m[jkil];// :143-149
+            } else
+                val = ab[ikjl];// :151-155
+        } else if (si == sl && sj == sk && si != sj) {
+            val = -ab[jkil];// :157-161
+        }
+        so[lin] = val;// the remaining spin patterns are the zero-initialised ones
+    }
+}
+void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, double *so) {
+    const long long total = 16LL * n * n * n * n;
+    if (total == 0) return;
+    to_so_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(aa, bb, ab, n, so);
+    ctx.launched("to_so");
+}
+
+__global__ void slice_kernel(const double *__restrict__ so, long long n2, int e0, int e1, int e2, int e3, int m0,
+                             int m1, int m2, int m3, double *__restrict__ out) {
+    const long long total = (long long) e0 * e1 * e2 * e3;
+    GRID_STRIDE(lin, total) {
+        long long r = lin;
+        const int s = (int) (r % e3);
+        r /= e3;
+        const int q3 = (int) (r % e2);
+        r /= e2;
+        const int q2 = (int) (r % e1);
+        const int p = (int) (r / e1);
+        out[lin] = so[(((p + m0) * n2 + (q2 + m1)) * n2 + (q3 + m2)) * n2 + (s + m3)];
+    }
+}
+void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *spec, double *out) {
+    QCP2_REQUIRE(spec && strlen(spec) == 4, "slice_ints: spec must have 4 characters");
+    int e[4], m[4];
+    for (int d = 0; d < 4; ++d) {
+        QCP2_REQUIRE(spec[d] == 'o' || spec[d] == 'v', "slice_ints: spec characters must be 'o' or 'v'");
+        e[d] = spec[d] == 'o' ? o : v;
+        m[d] = spec[d] == 'v' ? o : 0;
+    }
+    QCP2_REQUIRE(o + v <= n2, "slice_ints: o + v exceeds the spin-orbital count");
+    const long long total = (long long) e[0] * e[1] * e[2] * e[3];
+    if (total == 0) return;
+    slice_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(so, n2, e[0], e[1], e[2], e[3],
+                                                                                 m[0], m[1], m[2], m[3], out);
+    ctx.launched("slice");
+}
+
+__global__ void denom_from_F_kernel(const double *__restrict__ F, long long n2, int o, int v,
+                                    double *__restrict__ d) {
+    const long long total = (long long) o * o * v * v;
+    GRID_STRIDE(lin, total) {
+        long long r = lin;
+        const int b = (int) (r % v);
+        r /= v;
+        const int a = (int) (r % v);
+        r /= v;
+        const int j = (int) (r % o);
+        const int i = (int) (r / o);
+        d[lin] = F[i * n2 + i] + F[j * n2 + j] - F[(o + a) * n2 + (o + a)] - F[(o + b) * n2 + (o + b)];
+    }
+}
+void make_denom(Ctx &ctx, const double *F_spin, int n2, int o, int v, double *denom) {
+    const long long total = (long long) o * o * v * v;
+    if (total == 0) return;
+    denom_from_F_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(F_spin, n2, o, v, denom);
+    ctx.launched("make_denom");
+}
+
+__global__ void so_moes_kernel(const double *__restrict__ ea, const double *__restrict__ eb, int n,
+                               double *__restrict__ F) {
+    const long long n2 = 2LL * n, total = n2 * n2;
+    GRID_STRIDE(lin, total) {
+        const long long i = lin / n2, j = lin % n2;
+        F[lin] = (i == j) ? ((i & 1) ? eb[i >> 1] : ea[i >> 1]) : 0.0;
+    }
+}
+void make_so_moes(Ctx &ctx, const double *ea, const double *eb, int n, double *F) {
+    const long long total = 4LL * n * n;
+    if (total == 0) return;
+    so_moes_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(ea, eb, n, F);
+    ctx.launched("make_so_moes");
+}
+
+__global__ void fock_kernel(const double *__restrict__ e1, const double *__restrict__ e2, int n1, int dim,
+                            double *__restrict__ F) {
+    const long long total = (long long) dim * dim;
+    GRID_STRIDE(lin, total) {
+        const long long i = lin / dim, j = lin % dim;
+        double val = 0.0;
+        if (i == j) {
+            const long long base = (n1 % 2 == 0) ? n1 / 2 + i / 2 : n1 / 2 + i / 2 + 1;// cc.cpp:28-31
+            val = (i % 2 == 0) ? e1[base] : e2[base];
+        }
+        F[lin] = val;
+    }
+}
+void make_fock(Ctx &ctx, const double *e1, const double *e2, int n1, int n2, double *F) {
+    const int dim = n2 - n1;
+    if (dim <= 0) return;
+    fock_kernel<<<grid_for((long long) dim * dim, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(e1, e2, n1, dim, F);
+    ctx.launched("make_fock");
+}
+
+// ---------------------------------------------------------------------------------
+// deterministic reductions
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double ws[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) ws[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? ws[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;// valid in thread 0
+}
+__global__ void finish_sum_kernel(const double *__restrict__ partial, int n, double *__restrict__ out) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
+    v = block_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
+}
+
+__global__ void mp2_kernel(const double *__restrict__ oovv, const double *__restrict__ denom, long long n,
+                           double *__restrict__ T, double *__restrict__ partial) {
+    double e = 0.0;
+    GRID_STRIDE(i, n) {
+        const double g = oovv[i], d = denom[i];
+        if (T) T[i] = g / d;
+        e += 0.25 * (g * g) / d;// mp2.cpp:33-34
+    }
+    e = block_sum(e);
+    if (threadIdx.x == 0) partial[blockIdx.x] = e;
+}
+void mp2_amplitudes_energy(Ctx &ctx, const double *oovv, const double *denom, long long n, double *T,
+                           double *e_dev) {
+    DBuf partial(ctx, kRedBlocks);
+    mp2_kernel<<<kRedBlocks, kBlock, 0, ctx.stream>>>(oovv, denom, n, T, partial);
+    ctx.launched("mp2");
+    finish_sum_kernel<<<1, kBlock, 0, ctx.stream>>>(partial, kRedBlocks, e_dev);
+    ctx.launched("finish_sum");
+}
+
+__global__ void ccsd_energy_kernel(const double *__restrict__ ts, const double *__restrict__ td,
+                                   const double *__restrict__ oovv, const double *__restrict__ fov, int o, int v,
+                                   double *__restrict__ partial) {
+    const long long n = (long long) o * o * v * v, n1 = (long long) o * v;
+    double e = 0.0;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        const int b = (int) (r % v);
+        r /= v;
+        const int a = (int) (r % v);
+        r /= v;
+        const int j = (int) (r % o);
+        const int i = (int) (r / o);
+        const double g = oovv[lin];
+        e += 0.25 * g * td[lin] + 0.5 * g * ts[i * v + a] * ts[j * v + b];// cc.cpp:399
+        if (fov != nullptr && lin < n1) e += fov[lin] * ts[lin];         // cc.cpp:396
+    }
+    e = block_sum(e);
+    if (threadIdx.x == 0) partial[blockIdx.x] = e;
+}
+void ccsd_energy(Ctx &ctx, const double *Ts, const double *Td, const double *oovv, const double *fov, int o, int v,
+                 double *e_dev) {
+    DBuf partial(ctx, kRedBlocks);
+    ccsd_energy_kernel<<<kRedBlocks, kBlock, 0, ctx.stream>>>(Ts, Td, oovv, fov, o, v, partial);
+    ctx.launched("ccsd_energy");
+    finish_sum_kernel<<<1, kBlock, 0, ctx.stream>>>(partial, kRedBlocks, e_dev);
+    ctx.launched("finish_sum");
+}
+
+// ---------------------------------------------------------------------------------
+// cc.cpp elementwise pieces
+// ---------------------------------------------------------------------------------
+__global__ void tau_kernel(const double *__restrict__ ts, const double *__restrict__ td, int o, int v, int bar,
+                           double *__restrict__ out) {
+    const long long n = (long long) o * o * v * v;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        const int b = (int) (r % v);
+        r /= v;
+        const int a = (int) (r % v);
+        r /= v;
+        const int j = (int) (r % o);
+        const int i = (int) (r / o);
+        const double x = ts[i * v + a] * ts[j * v + b], y = ts[i * v + b] * ts[j * v + a];
+        out[lin] = bar ? td[lin] + 0.5 * (x - y) : td[lin] + x - y;// Stanton eqs. 10 / 9
+    }
+}
+void make_tau(Ctx &ctx, const double *Ts, const double *Td, int o, int v, bool bar, double *out) {
+    const long long n = (long long) o * o * v * v;
+    if (n == 0) return;
+    tau_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(Ts, Td, o, v, bar ? 1 : 0, out);
+    ctx.launched("make_tau");
+}
+
+__global__ void multiply_ts_kernel(const double *__restrict__ ts, int o, int v, double *__restrict__ out) {
+    const long long n = (long long) o * v * o * v, ov = (long long) o * v;
+    GRID_STRIDE(lin, n) out[lin] = ts[lin / ov] * ts[lin % ov];// out[j,f,n,b] = t[j,f] t[n,b]
+}
+void multiply_Ts(Ctx &ctx, const double *Ts, int o, int v, double *out) {
+    const long long n = (long long) o * v * o * v;
+    if (n == 0) return;
+    multiply_ts_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(Ts, o, v, out);
+    ctx.launched("multiply_Ts");
+}
+
+__global__ void add_offdiag_kernel(double *__restrict__ F, const double *__restrict__ add, int n) {
+    const long long total = (long long) n * n;
+    GRID_STRIDE(lin, total) {
+        if (lin / n != lin % n) F[lin] += add[lin];
+    }
+}
+void add_offdiag(Ctx &ctx, double *F, const double *Fadd, int n) {
+    if (n <= 0) return;
+    add_offdiag_kernel<<<grid_for((long long) n * n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(F, Fadd, n);
+    ctx.launched("add_offdiag");
+}
+
+__global__ void d_ia_kernel(const double *__restrict__ r, const double *__restrict__ foo,
+                            const double *__restrict__ fvv, int o, int v, double *__restrict__ out) {
+    const long long n = (long long) o * v;
+    GRID_STRIDE(lin, n) {
+        const int i = (int) (lin / v), a = (int) (lin % v);
+        const double d = foo[(long long) i * o + i] - fvv[(long long) a * v + a];
+        out[lin] = r ? r[lin] / d : d;
+    }
+}
+__global__ void d_ijab_kernel(const double *__restrict__ r, const double *__restrict__ foo,
+                              const double *__restrict__ fvv, int o, int v, double *__restrict__ out) {
+    const long long n = (long long) o * o * v * v;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        const int b = (int) (q % v);
+        q /= v;
+        const int a = (int) (q % v);
+        q /= v;
+        const int j = (int) (q % o);
+        const int i = (int) (q / o);
+        const double d = foo[(long long) i * o + i] + foo[(long long) j * o + j] - fvv[(long long) a * v + a] -
+                         fvv[(long long) b * v + b];
+        out[lin] = r ? r[lin] / d : d;
+    }
+}
+__global__ void d_triples_kernel(const double *__restrict__ foo, const double *__restrict__ fvv, int o, int v,
+                                 double *__restrict__ out) {
+    const long long n = (long long) o * o * o * v * v * v;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        const int c = (int) (q % v);
+        q /= v;
+        const int b = (int) (q % v);
+        q /= v;
+        const int a = (int) (q % v);
+        q /= v;
+        const int k = (int) (q % o);
+        q /= o;
+        const int j = (int) (q % o);
+        const int i = (int) (q / o);
+        out[lin] = foo[(long long) i * o + i] + foo[(long long) j * o + j] + foo[(long long) k * o + k] -
+                   fvv[(long long) a * v + a] - fvv[(long long) b * v + b] - fvv[(long long) c * v + c];
+    }
+}
+void make_D_ia(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D) {
+    divide_D_ia(ctx, nullptr, foo, fvv, o, v, D);
+}
+void make_D_ijab(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D) {
+    divide_D_ijab(ctx, nullptr, foo, fvv, o, v, D);
+}
+void make_D_triples(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D) {
+    const long long n = (long long) o * o * o * v * v * v;
+    if (n == 0) return;
+    d_triples_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(foo, fvv, o, v, D);
+    ctx.launched("make_D_triples");
+}
+void divide_D_ia(Ctx &ctx, const double *r, const double *foo, const double *fvv, int o, int v, double *out) {
+    const long long n = (long long) o * v;
+    if (n == 0) return;
+    d_ia_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(r, foo, fvv, o, v, out);
+    ctx.launched("D_ia");
+}
+void divide_D_ijab(Ctx &ctx, const double *r, const double *foo, const double *fvv, int o, int v, double *out) {
+    const long long n = (long long) o * o * v * v;
+    if (n == 0) return;
+    d_ijab_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(r, foo, fvv, o, v, out);
+    ctx.launched("D_ijab");
+}
+
+__global__ void diag_kernel(const double *__restrict__ F, int n, double *__restrict__ d) {
+    GRID_STRIDE(i, (long long) n) d[i] = F[i * n + i];
+}
+void extract_diag(Ctx &ctx, const double *F, int n, double *d) {
+    if (n <= 0) return;
+    diag_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(F, n, d);
+    ctx.launched("extract_diag");
+}
+
+// ---------------------------------------------------------------------------------
+// antisymmetry check (selects the symmetric (T) path)
+// ---------------------------------------------------------------------------------
+__global__ void antisym_kernel(const double *__restrict__ x, long long d0, long long d1, long long d2, long long d3,
+                               int pair, unsigned long long *__restrict__ res) {
+    const long long n = d0 * d1 * d2 * d3;
+    double defect = 0.0, mx = 0.0;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        const long long i3 = r % d3;
+        r /= d3;
+        const long long i2 = r % d2;
+        r /= d2;
+        const long long i1 = r % d1;
+        const long long i0 = r / d1;
+        const long long other = pair == 0 ? ((i1 * d1 + i0) * d2 + i2) * d3 + i3 : ((i0 * d1 + i1) * d2 + i3) * d3 + i2;
+        const double a = x[lin];
+        defect = fmax(defect, fabs(a + x[other]));
+        mx = fmax(mx, fabs(a));
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        defect = fmax(defect, __shfl_xor_sync(0xffffffffu, defect, s));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    }
+    if ((threadIdx.x & 31) == 0) {// non-negative doubles order like their bit patterns
+        atomicMax(res, (unsigned long long) __double_as_longlong(defect));
+        atomicMax(res + 1, (unsigned long long) __double_as_longlong(mx));
+    }
+}
+void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,
+                         double *defect, double *maxabs) {
+    if (pair == 0) QCP2_REQUIRE(d0 == d1, "antisymmetry check: extents differ");
+    else QCP2_REQUIRE(d2 == d3, "antisymmetry check: extents differ");
+    unsigned long long *res = static_cast<unsigned long long *>(ctx.alloc_bytes(16));
+    QCP2_CUDA(cudaMemsetAsync(res, 0, 16, ctx.stream));
+    const long long n = d0 * d1 * d2 * d3;
+    if (n > 0) {
+        antisym_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(x, d0, d1, d2, d3, pair, res);
+        ctx.launched("antisym");
+    }
+    unsigned long long h[2];
+    QCP2_CUDA(cudaMemcpyAsync(h, res, 16, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    ctx.free(res);
+    long long b0 = (long long) h[0], b1 = (long long) h[1];
+    memcpy(defect, &b0, 8);
+    memcpy(maxabs, &b1, 8);
+}
+
+}// namespace qcp2

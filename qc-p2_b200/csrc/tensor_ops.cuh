@@ -1,0 +1,40 @@
+// tensor_ops.cuh -- bandwidth-bound tensor kernels: permutation (transpose) with axpby,
+// elementwise amplitude algebra, denominators, gathers and deterministic reductions.
+#pragma once
+#include "common.cuh"
+
+namespace qcp2 {
+
+// out[o0..o_{r-1}] = beta*out + alpha*in[sum_d o_d * istride[d]]   (out dense row-major)
+void permute_axpby(Ctx &ctx, double *out, const double *in, int rank, const long long *out_ext,
+                   const long long *in_stride_per_out_dim, double alpha, double beta);
+// out = alpha*x + beta*out (n elements)
+void axpby(Ctx &ctx, double *out, const double *x, double alpha, double beta, long long n);
+void fill_zero(Ctx &ctx, double *p, long long n);
+
+// integrals.cpp / mp2.cpp
+void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, double *so);
+void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *spec, double *out);
+void make_denom(Ctx &ctx, const double *F_spin, int n2, int o, int v, double *denom);
+void make_so_moes(Ctx &ctx, const double *ea, const double *eb, int n, double *F);
+void mp2_amplitudes_energy(Ctx &ctx, const double *oovv, const double *denom, long long n, double *T, double *e_dev);
+void make_fock(Ctx &ctx, const double *e1, const double *e2, int n1, int n2, double *F);
+
+// cc.cpp elementwise pieces
+void make_tau(Ctx &ctx, const double *Ts, const double *Td, int o, int v, bool bar, double *out);
+void multiply_Ts(Ctx &ctx, const double *Ts, int o, int v, double *out);
+void add_offdiag(Ctx &ctx, double *F, const double *Fadd, int n);// F(a,e) += (1-d_ae) Fadd(a,e)
+void make_D_ia(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);
+void make_D_ijab(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);
+void make_D_triples(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);
+void divide_D_ia(Ctx &ctx, const double *r, const double *foo, const double *fvv, int o, int v, double *out);
+void divide_D_ijab(Ctx &ctx, const double *r, const double *foo, const double *fvv, int o, int v, double *out);
+void ccsd_energy(Ctx &ctx, const double *Ts, const double *Td, const double *oovv, const double *fov, int o, int v,
+                 double *e_dev);
+void extract_diag(Ctx &ctx, const double *F, int n, double *d);
+
+// max |x + P x| over an index-pair transposition, relative to max|x| -> host values
+void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,
+                         double *defect, double *maxabs);
+
+}// namespace qcp2

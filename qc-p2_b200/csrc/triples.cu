@@ -1,0 +1,497 @@
+// triples.cu -- (T) energy, cc.cpp:454-560, restated per occupied triple (i,j,k):
+//
+//   A[a,:]  = [ T2[j,k,a,:] | -T2[i,k,a,:] | -T2[j,i,a,:] | -ovoo[:,a,j,k] | ovoo[:,a,i,k] | ovoo[:,a,j,i] ]
+//   B[:,bc] = [ vovv[:,i,b,c] ; vovv[:,j,b,c] ; vovv[:,k,b,c] ; T2[i,:,b,c] ; T2[j,:,b,c] ; T2[k,:,b,c] ]
+//   X = A.B                                   (cc.cpp:501,505,509,513,517,521: one GEMM, K = 3(v+o))
+//   W[a,b,c] = X[a,b,c] - X[b,a,c] - X[c,b,a] (the other twelve contract calls, cc.cpp:502-523)
+//   Y[a,b,c] = t_ia<jk||bc> - t_ja<ik||bc> - t_ka<ji||bc>,  V = Y - Y[b,a,c] - Y[c,b,a]   (cc.cpp:479-489)
+//   E(T) = 1/36 sum_ijk sum_abc W (W + V) / D_ijkabc                                       (cc.cpp:541-556)
+//
+// LITERAL mode sums all o^3 ordered triples and all v^3 (a,b,c) and assumes nothing about
+// the inputs (this is what the as-written UHF path needs).  SYMMETRIC mode
+// requires the physical antisymmetries of T2, <oo||vv>, <vo||vv>, <ov||oo>, packs b<c
+// columns, visits i<j<k and a<b<c only and weights by 36/36.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../include/qcp2_b200.h"
+#include "tensor_ops.cuh"
+#include "triples.cuh"
+
+namespace qcp2 {
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kBTile = 8;// b values per energy block (one per warp)
+
+#define GRID_STRIDE(lin, n) \
+    for (long long lin = (long long) blockIdx.x * blockDim.x + threadIdx.x; lin < (n); lin += (long long) gridDim.x * blockDim.x)
+
+__host__ __device__ __forceinline__ long long pair_index(long long b, long long c, long long v) {
+    return b * v - b * (b + 1) / 2 + (c - b - 1);// b < c
+}
+
+// dst[(r1,r0) or (r0,r1)][p(b<c)] = src[r0][r1][b][c]
+__global__ void pack_bc_kernel(const double *__restrict__ src, long long R0, long long R1, int swap01, int v,
+                               double *__restrict__ dst) {
+    const long long np = (long long) v * (v - 1) / 2, n = R0 * R1 * v * v;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        const long long c = r % v;
+        r /= v;
+        const long long b = r % v;
+        r /= v;
+        if (b >= c) continue;
+        const long long r1 = r % R1, r0 = r / R1;
+        const long long row = swap01 ? r1 * R0 + r0 : r0 * R1 + r1;
+        dst[row * np + pair_index(b, c, v)] = src[lin];
+    }
+}
+
+struct BuildAArgs {
+    const double *T2, *ovoo;
+    const int *ijk;
+    double *A;
+    int o, v, kpad, count;
+    int kb_begin[GEMM_MAX_SEG + 1];
+};
+
+__global__ void build_A_kernel(BuildAArgs p) {
+    const long long per = (long long) p.v * p.kpad, n = per * p.count;
+    const long long O = p.o, V = p.v;
+    GRID_STRIDE(lin, n) {
+        const int t = (int) (lin / per);
+        const long long rem = lin - (long long) t * per;
+        const long long a = rem / p.kpad;
+        const int col = (int) (rem - a * p.kpad);
+        const int i = p.ijk[3 * t], j = p.ijk[3 * t + 1], k = p.ijk[3 * t + 2];
+        int s = 0;
+#pragma unroll
+        for (int q = 1; q < GEMM_MAX_SEG; ++q)
+            if (col >= p.kb_begin[q] * GEMM_BK) s = q;
+        const long long r = col - p.kb_begin[s] * GEMM_BK;
+        double val = 0.0;
+        if (s < 3) {
+            if (r < V) {
+                const long long x = s == 0 ? j : (s == 1 ? i : j), y = s == 0 ? k : (s == 1 ? k : i);
+                val = p.T2[((x * O + y) * V + a) * V + r];
+                if (s != 0) val = -val;
+            }
+        } else if (r < O) {
+            const long long x = s == 3 ? j : (s == 4 ? i : j), y = s == 3 ? k : (s == 4 ? k : i);
+            val = p.ovoo[((r * V + a) * O + x) * O + y];
+            if (s == 3) val = -val;
+        }
+        p.A[lin] = val;
+    }
+}
+
+struct EnergyArgs {
+    const double *X;        // [count][v][ncols]
+    const double *T1;       // [o][v]
+    const double *oovv;     // packed [o][o][np] or dense [o][o][v][v]
+    const double *eo, *ev;
+    const int *ijk;
+    double *partial;        // [count][blocks_per_triple]
+    int o, v, nbt;
+    long long ncols;
+};
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) x += __shfl_xor_sync(0xffffffffu, x, s);
+    return x;
+}
+
+// One block per (a, tile of 8 b values); warp w owns b = 8*bt + w, lanes sweep c.
+template<bool PACKED>
+__global__ void __launch_bounds__(kBlock) t_energy_kernel(EnergyArgs p) {
+    __shared__ double ws[kBlock / 32];
+    const int t = blockIdx.z;
+    const int a = blockIdx.x / p.nbt, bt = blockIdx.x % p.nbt;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = bt * kBTile + warp;
+    const long long V = p.v, O = p.o, nc = p.ncols;
+    const int i = p.ijk[3 * t], j = p.ijk[3 * t + 1], k = p.ijk[3 * t + 2];
+    const double *X = p.X + (long long) t * V * nc;
+    double sum = 0.0;
+    const bool active = PACKED ? (b < p.v && a < b) : (b < p.v);
+    if (active) {
+        const long long blk = PACKED ? nc : V * V;
+        const double *Ojk = p.oovv + (j * O + k) * blk, *Oik = p.oovv + (i * O + k) * blk,
+                     *Oji = p.oovv + (j * O + i) * blk;
+        const double tia = p.T1[i * V + a], tja = p.T1[j * V + a], tka = p.T1[k * V + a];
+        const double tib = p.T1[i * V + b], tjb = p.T1[j * V + b], tkb = p.T1[k * V + b];
+        const double dab = p.eo[i] + p.eo[j] + p.eo[k] - p.ev[a] - p.ev[b];
+        if (PACKED) {
+            const long long pab = pair_index(a, b, V);
+            const double ojk_ab = Ojk[pab], oik_ab = Oik[pab], oji_ab = Oji[pab];
+            const double *Xa = X + a * nc, *Xb = X + b * nc;
+            for (int c = b + 1 + lane; c < p.v; c += 32) {
+                const long long pbc = pair_index(b, c, V), pac = pair_index(a, c, V);
+                const double W = Xa[pbc] - Xb[pac] + X[c * nc + pab];
+                const double tic = p.T1[i * V + c], tjc = p.T1[j * V + c], tkc = p.T1[k * V + c];
+                const double Ya = tia * Ojk[pbc] - tja * Oik[pbc] - tka * Oji[pbc];
+                const double Yb = tib * Ojk[pac] - tjb * Oik[pac] - tkb * Oji[pac];
+                const double Yc = tic * ojk_ab - tjc * oik_ab - tkc * oji_ab;
+                const double Vv = Ya - Yb + Yc;
+                sum += W * (W + Vv) / (dab - p.ev[c]);
+            }
+        } else {
+            const double *Xab = X + (a * V + b) * V, *Xba = X + (b * V + a) * V;
+            const double *ojk_bc = Ojk + b * V, *oik_bc = Oik + b * V, *oji_bc = Oji + b * V;
+            const double *ojk_ac = Ojk + a * V, *oik_ac = Oik + a * V, *oji_ac = Oji + a * V;
+            for (int c = lane; c < p.v; c += 32) {
+                const double W = Xab[c] - Xba[c] - X[(c * V + b) * V + a];
+                const double tic = p.T1[i * V + c], tjc = p.T1[j * V + c], tkc = p.T1[k * V + c];
+                const double Ya = tia * ojk_bc[c] - tja * oik_bc[c] - tka * oji_bc[c];
+                const double Yb = tib * ojk_ac[c] - tjb * oik_ac[c] - tkb * oji_ac[c];
+                const double Yc = tic * Ojk[b * V + a] - tjc * Oik[b * V + a] - tkc * Oji[b * V + a];
+                const double Vv = Ya - Yb - Yc;
+                sum += W * (W + Vv) / (dab - p.ev[c]);
+            }
+        }
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) ws[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) s += ws[w];
+        p.partial[(long long) t * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// one block per triple: fixed-order sum of the block partials -> weighted triple energy
+__global__ void t_finish_kernel(const double *__restrict__ partial, int bpt, double weight, double *__restrict__ e_run,
+                                double *__restrict__ e_triples, const long long *__restrict__ gidx) {
+    __shared__ double ws[kBlock / 32];
+    const int t = blockIdx.x;
+    double s = 0.0;
+    for (int q = threadIdx.x; q < bpt; q += blockDim.x) s += partial[(long long) t * bpt + q];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) tot += ws[w];
+        tot *= weight;
+        e_run[t] = tot;
+        if (e_triples) e_triples[gidx[t]] = tot;
+    }
+}
+
+// ---- synthetic inputs ---------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    unsigned long long z = x + 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u_rand(unsigned long long seed, unsigned long long tag, unsigned long long idx) {
+    const unsigned long long z = splitmix64(seed ^ (tag << 56) ^ idx);
+    return (double) (z >> 11) * 0x1.0p-52 - 1.0;
+}
+
+// kind 0: plain [n]; 1: antisymmetric in (0,1) and (2,3) of [o,o,v,v]; 2: antisymmetric in
+// the last pair of [d0,d1,d2,d2]
+__global__ void synth_kernel(double *__restrict__ out, int kind, long long d0, long long d1, long long d2,
+                             long long d3, unsigned long long seed, unsigned long long tag, double scale) {
+    const long long n = d0 * d1 * d2 * d3;
+    GRID_STRIDE(lin, n) {
+        double val;
+        if (kind == 0) {
+            val = scale * u_rand(seed, tag, (unsigned long long) lin);
+        } else {
+            long long r = lin;
+            long long i3 = r % d3;
+            r /= d3;
+            long long i2 = r % d2;
+            r /= d2;
+            long long i1 = r % d1;
+            long long i0 = r / d1;
+            double sign = 1.0;
+            if (i2 == i3) sign = 0.0;
+            if (i2 > i3) {
+                const long long tmp = i2;
+                i2 = i3, i3 = tmp, sign = -sign;
+            }
+            if (kind == 1) {
+                if (i0 == i1) sign = 0.0;
+                if (i0 > i1) {
+                    const long long tmp = i0;
+                    i0 = i1, i1 = tmp, sign = -sign;
+                }
+            }
+            const unsigned long long canon = (unsigned long long) (((i0 * d1 + i1) * d2 + i2) * d3 + i3);
+            val = sign == 0.0 ? 0.0 : sign * scale * u_rand(seed, tag, canon);
+        }
+        out[lin] = val;
+    }
+}
+__global__ void ramp_kernel(double *__restrict__ out, int n, double lo, double span) {
+    GRID_STRIDE(i, (long long) n) out[i] = lo + span * (double) i / (double) (n > 1 ? n - 1 : 1);
+}
+
+}// namespace
+
+void synth_t_inputs(Ctx &ctx, int o, int v, unsigned long long seed, double *T1, double *T2, double *oovv, double *vovv,
+                    double *ovoo, double *eps_o, double *eps_v) {
+    auto launch = [&](double *out, int kind, long long d0, long long d1, long long d2, long long d3,
+                      unsigned long long tag, double scale) {
+        const long long n = d0 * d1 * d2 * d3;
+        if (n == 0 || !out) return;
+        synth_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(out, kind, d0, d1, d2, d3, seed, tag,
+                                                                                 scale);
+        ctx.launched("synth");
+    };
+    launch(T1, 0, 1, 1, o, v, 1, 0.05);
+    launch(T2, 1, o, o, v, v, 2, 0.02);
+    launch(oovv, 1, o, o, v, v, 3, 0.1);
+    launch(vovv, 2, v, o, v, v, 4, 0.1);
+    launch(ovoo, 2, o, v, o, o, 5, 0.1);
+    if (eps_o) {
+        ramp_kernel<<<1, kBlock, 0, ctx.stream>>>(eps_o, o, -2.0, 1.5);
+        ctx.launched("ramp");
+    }
+    if (eps_v) {
+        ramp_kernel<<<grid_for(v, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(eps_v, v, 0.1, 2.9);
+        ctx.launched("ramp");
+    }
+}
+
+long long t_count(int o, int mode) {
+    const long long O = o;
+    return mode == QCP2_T_SYMMETRIC ? O * (O - 1) * (O - 2) / 6 : O * O * O;
+}
+
+int t_select_mode(Ctx &ctx, const double *T2, const double *oovv, const double *vovv, const double *ovoo, int o,
+                  int v) {
+    const double tol = 1e-10;
+    double d, m;
+    auto ok = [&](const double *x, long long d0, long long d1, long long d2, long long d3, int pair) {
+        antisymmetry_defect(ctx, x, d0, d1, d2, d3, pair, &d, &m);
+        return d <= tol * m;
+    };
+    const bool sym = ok(T2, o, o, v, v, 0) && ok(T2, o, o, v, v, 1) && ok(oovv, o, o, v, v, 0) &&
+                     ok(oovv, o, o, v, v, 1) && ok(vovv, v, o, v, v, 1) && ok(ovoo, o, v, o, o, 1);
+    return sym ? QCP2_T_SYMMETRIC : QCP2_T_LITERAL;
+}
+
+TPlan::~TPlan() {
+    if (ctx) {
+        cudaStreamSynchronize(ctx->stream);
+        if (aux) cudaStreamSynchronize(aux);
+    }
+    for (int s = 0; s < 2; ++s) {
+        if (gemm_done[s]) cudaEventDestroy(gemm_done[s]);
+        if (energy_done[s]) cudaEventDestroy(energy_done[s]);
+    }
+    if (t_begin) cudaEventDestroy(t_begin);
+    if (t_end) cudaEventDestroy(t_end);
+    for (cudaEvent_t e : gemm_ev) cudaEventDestroy(e);
+    if (seg_dev) cudaFree(seg_dev);
+    if (ijk_dev) cudaFree(ijk_dev);
+    if (aux) cudaStreamDestroy(aux);
+}
+
+TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode) {
+    QCP2_REQUIRE(mode == QCP2_T_LITERAL || mode == QCP2_T_SYMMETRIC, "(T): mode must be LITERAL or SYMMETRIC");
+    QCP2_REQUIRE(o >= 1 && v >= 1, "(T): o and v must be positive");
+    std::unique_ptr<TPlan> P(new TPlan());
+    P->ctx = &ctx, P->o = o, P->v = v, P->mode = mode;
+    const long long O = o, V = v;
+    const bool sym = mode == QCP2_T_SYMMETRIC;
+    P->ncols = sym ? V * (V - 1) / 2 : V * V;
+    P->ntriples = t_count(o, mode);
+    P->T1 = T1, P->T2 = T2, P->oovv = oovv, P->vovv = vovv, P->ovoo = ovoo;
+    P->eo = DBuf(ctx, (size_t) o), P->ev = DBuf(ctx, (size_t) v);
+    QCP2_CUDA(cudaMemcpyAsync(P->eo.p, eps_o, (size_t) o * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    QCP2_CUDA(cudaMemcpyAsync(P->ev.p, eps_v, (size_t) v * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    for (int s = 0; s < GEMM_MAX_SEG; ++s)
+        P->kb_begin[s + 1] = P->kb_begin[s] + (int) (((s < 3 ? V : O) + GEMM_BK - 1) / GEMM_BK);
+    P->kpad = P->kb_begin[GEMM_MAX_SEG] * GEMM_BK;
+    if (sym && P->ncols > 0) {
+        const long long np = P->ncols;
+        P->vovvP = DBuf(ctx, (size_t) (O * V * np));
+        P->T2P = DBuf(ctx, (size_t) (O * O * np));
+        P->oovvP = DBuf(ctx, (size_t) (O * O * np));
+        auto pack = [&](const double *src, long long R0, long long R1, int swap, double *dst) {
+            pack_bc_kernel<<<grid_for(R0 * R1 * V * V, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(src, R0, R1, swap,
+                                                                                                   v, dst);
+            ctx.launched("pack_bc");
+        };
+        pack(vovv, V, O, 1, P->vovvP);// [e][i][b][c] -> [i][e][p]
+        pack(T2, O, O, 0, P->T2P);    // [i][m][b][c] -> [i][m][p]
+        pack(oovv, O, O, 0, P->oovvP);
+    }
+    // batch size: enough CTAs for ~48 full waves, bounded by a 4 GB X buffer
+    const long long tiles = ((V + TileT::kBM - 1) / TileT::kBM) * ((std::max<long long>(P->ncols, 1) + TileT::kBN - 1) / TileT::kBN);
+    long long tb = (48LL * ctx.sm_count + tiles - 1) / tiles;
+    const long long xbytes = std::max<long long>(V * P->ncols * 8, 8);
+    tb = std::min(tb, std::max<long long>(1, (4LL << 30) / xbytes));
+    tb = std::max<long long>(1, std::min<long long>(tb, std::min<long long>(4096, std::max<long long>(P->ntriples, 1))));
+    P->tb = (int) tb;
+    P->blocks_per_triple = v * ((v + kBTile - 1) / kBTile);
+    for (int s = 0; s < 2; ++s) {
+        P->Abuf[s] = DBuf(ctx, (size_t) (tb * V * P->kpad));
+        P->Xbuf[s] = DBuf(ctx, (size_t) (tb * V * std::max<long long>(P->ncols, 1)));
+        P->partial[s] = DBuf(ctx, (size_t) (tb * P->blocks_per_triple));
+        QCP2_CUDA(cudaEventCreateWithFlags(&P->gemm_done[s], cudaEventDisableTiming));
+        QCP2_CUDA(cudaEventCreateWithFlags(&P->energy_done[s], cudaEventDisableTiming));
+    }
+    QCP2_CUDA(cudaEventCreate(&P->t_begin));
+    QCP2_CUDA(cudaEventCreate(&P->t_end));
+    QCP2_CUDA(cudaStreamCreateWithFlags(&P->aux, cudaStreamNonBlocking));
+    ctx.sync();
+    return P.release();
+}
+
+static void triple_of(long long t, int o, bool sym, int *ijk) {
+    if (!sym) {
+        ijk[2] = (int) (t % o), ijk[1] = (int) ((t / o) % o), ijk[0] = (int) (t / ((long long) o * o));
+        return;
+    }
+    // lexicographic i<j<k: walk i then j (o is small)
+    long long rem = t;
+    for (int i = 0; i < o - 2; ++i) {
+        const long long ni = (long long) (o - i - 1) * (o - i - 2) / 2;
+        if (rem >= ni) {
+            rem -= ni;
+            continue;
+        }
+        for (int j = i + 1; j < o - 1; ++j) {
+            const long long nj = o - j - 1;
+            if (rem >= nj) {
+                rem -= nj;
+                continue;
+            }
+            ijk[0] = i, ijk[1] = j, ijk[2] = j + 1 + (int) rem;
+            return;
+        }
+    }
+    throw Error("(T): triple index out of range");
+}
+
+void t_plan_run(TPlan &P, long long first, long long stride, long long max_count, double *e_triples_dev,
+                double *energy_host) {
+    Ctx &ctx = *P.ctx;
+    QCP2_REQUIRE(first >= 0 && stride >= 1, "(T): bad triple range");
+    long long count = first < P.ntriples ? (P.ntriples - first + stride - 1) / stride : 0;
+    if (max_count >= 0) count = std::min(count, max_count);
+    *energy_host = 0.0;
+    P.last_gemm_seconds = P.last_total_seconds = 0.0;
+    P.last_gemm_launches = 0;
+    const long long launches0 = ctx.launches;
+    if (count == 0 || P.ncols == 0) return;
+    const bool sym = P.mode == QCP2_T_SYMMETRIC;
+    const long long O = P.o, V = P.v, nc = P.ncols;
+
+    // host-side descriptors for the whole run
+    std::vector<int> ijk((size_t) (3 * count));
+    std::vector<SegDesc> seg((size_t) count);
+    std::vector<long long> gidx((size_t) count);
+    bool aligned = true;
+    for (long long q = 0; q < count; ++q) {
+        const long long t = first + q * stride;
+        gidx[(size_t) q] = t;
+        int *x = &ijk[(size_t) (3 * q)];
+        triple_of(t, P.o, sym, x);
+        for (int s = 0; s < 3; ++s) {
+            const long long occ = x[s];
+            seg[(size_t) q].B[s] = sym ? P.vovvP.p + occ * V * nc : P.vovv + occ * V * V;
+            seg[(size_t) q].B[3 + s] = sym ? P.T2P.p + occ * O * nc : P.T2 + occ * O * V * V;
+        }
+        for (int s = 0; s < GEMM_MAX_SEG; ++s)
+            aligned = aligned && ((reinterpret_cast<uintptr_t>(seg[(size_t) q].B[s]) & 15) == 0);
+    }
+    if (P.run_capacity < count) {
+        if (P.seg_dev) cudaFree(P.seg_dev);
+        if (P.ijk_dev) cudaFree(P.ijk_dev);
+        P.seg_dev = nullptr, P.ijk_dev = nullptr;
+        QCP2_CUDA(cudaMalloc(&P.seg_dev, (size_t) count * sizeof(SegDesc)));
+        QCP2_CUDA(cudaMalloc(&P.ijk_dev, (size_t) count * 3 * sizeof(int)));
+        P.run_capacity = count;
+    }
+    DBuf e_run(ctx, (size_t) count);
+    long long *gidx_dev = static_cast<long long *>(ctx.alloc_bytes((size_t) count * 8));
+    QCP2_CUDA(cudaMemcpyAsync(P.seg_dev, seg.data(), (size_t) count * sizeof(SegDesc), cudaMemcpyHostToDevice, ctx.stream));
+    QCP2_CUDA(cudaMemcpyAsync(P.ijk_dev, ijk.data(), (size_t) count * 3 * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+    QCP2_CUDA(cudaMemcpyAsync(gidx_dev, gidx.data(), (size_t) count * 8, cudaMemcpyHostToDevice, ctx.stream));
+
+    const long long nbatch = (count + P.tb - 1) / P.tb;
+    while ((long long) P.gemm_ev.size() < 2 * nbatch) {
+        cudaEvent_t e;
+        QCP2_CUDA(cudaEventCreate(&e));
+        P.gemm_ev.push_back(e);
+    }
+    const double weight = sym ? 1.0 : 1.0 / 36.0;// 6 (ijk) x 6 (abc) / 36 for sorted triples
+    QCP2_CUDA(cudaEventRecord(P.t_begin, ctx.stream));
+    for (long long bq = 0; bq < nbatch; ++bq) {
+        const int s = (int) (bq & 1);
+        const long long off = bq * P.tb;
+        const int cnt = (int) std::min<long long>(P.tb, count - off);
+        if (bq >= 2) QCP2_CUDA(cudaStreamWaitEvent(ctx.stream, P.energy_done[s], 0));
+        BuildAArgs ba;
+        ba.T2 = P.T2, ba.ovoo = P.ovoo, ba.ijk = P.ijk_dev + 3 * off, ba.A = P.Abuf[s];
+        ba.o = P.o, ba.v = P.v, ba.kpad = P.kpad, ba.count = cnt;
+        for (int q = 0; q <= GEMM_MAX_SEG; ++q) ba.kb_begin[q] = P.kb_begin[q];
+        build_A_kernel<<<grid_for((long long) cnt * V * P.kpad, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(ba);
+        ctx.launched("build_A");
+
+        GemmArgs g;
+        g.M = P.v, g.N = (int) nc, g.K = P.kpad, g.batch = cnt;
+        g.A = P.Abuf[s], g.lda = P.kpad, g.strideA = V * P.kpad;
+        g.C = P.Xbuf[s], g.ldc = nc, g.strideC = V * nc;
+        g.seg = P.seg_dev + off, g.nseg = GEMM_MAX_SEG, g.seg_aligned = aligned;
+        for (int q = 0; q <= GEMM_MAX_SEG; ++q) g.seg_kb_begin[q] = P.kb_begin[q];
+        for (int q = 0; q < GEMM_MAX_SEG; ++q) {
+            g.seg_rows[q] = q < 3 ? P.v : P.o;
+            g.seg_ldb[q] = sym ? nc : (q < 3 ? O * V * V : V * V);
+        }
+        QCP2_CUDA(cudaEventRecord(P.gemm_ev[(size_t) (2 * bq)], ctx.stream));
+        gemm(ctx, g, true, true);
+        QCP2_CUDA(cudaEventRecord(P.gemm_ev[(size_t) (2 * bq + 1)], ctx.stream));
+        ++P.last_gemm_launches;
+        QCP2_CUDA(cudaEventRecord(P.gemm_done[s], ctx.stream));
+
+        QCP2_CUDA(cudaStreamWaitEvent(P.aux, P.gemm_done[s], 0));
+        EnergyArgs ea;
+        ea.X = P.Xbuf[s], ea.T1 = P.T1, ea.oovv = sym ? P.oovvP.p : P.oovv, ea.eo = P.eo, ea.ev = P.ev;
+        ea.ijk = P.ijk_dev + 3 * off, ea.partial = P.partial[s];
+        ea.o = P.o, ea.v = P.v, ea.nbt = (P.v + kBTile - 1) / kBTile, ea.ncols = nc;
+        dim3 grid((unsigned) P.blocks_per_triple, 1, (unsigned) cnt);
+        if (sym) t_energy_kernel<true><<<grid, kBlock, 0, P.aux>>>(ea);
+        else t_energy_kernel<false><<<grid, kBlock, 0, P.aux>>>(ea);
+        ctx.launched("t_energy");
+        t_finish_kernel<<<cnt, kBlock, 0, P.aux>>>(P.partial[s], P.blocks_per_triple, weight, e_run.p + off, e_triples_dev,
+                                                  gidx_dev + off);
+        ctx.launched("t_finish");
+        QCP2_CUDA(cudaEventRecord(P.energy_done[s], P.aux));
+    }
+    for (int s = 0; s < 2 && s < nbatch; ++s) QCP2_CUDA(cudaStreamWaitEvent(ctx.stream, P.energy_done[s], 0));
+    QCP2_CUDA(cudaEventRecord(P.t_end, ctx.stream));
+    std::vector<double> e_host((size_t) count);
+    QCP2_CUDA(cudaMemcpyAsync(e_host.data(), e_run.p, (size_t) count * 8, cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+    ctx.free(gidx_dev);
+    double tot = 0.0;
+    for (double x : e_host) tot += x;// fixed order: independent of batching and of the rank count
+    *energy_host = tot;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, P.t_begin, P.t_end);
+    P.last_total_seconds = ms * 1e-3;
+    for (long long bq = 0; bq < nbatch; ++bq) {
+        cudaEventElapsedTime(&ms, P.gemm_ev[(size_t) (2 * bq)], P.gemm_ev[(size_t) (2 * bq + 1)]);
+        P.last_gemm_seconds += ms * 1e-3;
+    }
+    P.last_all_launches = ctx.launches - launches0;
+}
+
+}// namespace qcp2

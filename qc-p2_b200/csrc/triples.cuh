@@ -1,0 +1,52 @@
+// triples.cuh -- perturbative triples (T), cc.cpp:454-560, evaluated one occupied triple at a
+// time: one segmented-K DMMA GEMM X = A.B (M = v, K = 3(v+o)) per triple plus a fused
+// permute-combine / denominator / energy sweep.  No o^3 v^3 tensor is ever materialised.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "dgemm.cuh"
+
+namespace qcp2 {
+
+struct TPlan {
+    Ctx *ctx = nullptr;
+    int o = 0, v = 0, mode = 0;     // mode: QCP2_T_LITERAL or QCP2_T_SYMMETRIC
+    long long ncols = 0;            // v*v (literal) or v(v-1)/2 (symmetric, b<c packed)
+    long long ntriples = 0;         // o^3 or C(o,3)
+    int kpad = 0;                   // padded K of the per-triple GEMM
+    int kb_begin[GEMM_MAX_SEG + 1] = {0, 0, 0, 0, 0, 0, 0};
+    // inputs (device).  literal mode reads the caller's tensors in place; symmetric mode
+    // owns b<c packed copies.
+    const double *T1 = nullptr, *T2 = nullptr, *oovv = nullptr, *vovv = nullptr, *ovoo = nullptr;
+    DBuf eo, ev, vovvP, T2P, oovvP;
+    // double-buffered per-batch workspace
+    int tb = 1;                     // triples per batch
+    DBuf Abuf[2], Xbuf[2], partial[2], ebatch[2];
+    SegDesc *seg_dev = nullptr;     // descriptors of the current run
+    int *ijk_dev = nullptr;
+    long long run_capacity = 0;
+    cudaStream_t aux = nullptr;
+    cudaEvent_t gemm_done[2] = {nullptr, nullptr}, energy_done[2] = {nullptr, nullptr};
+    cudaEvent_t t_begin = nullptr, t_end = nullptr;
+    std::vector<cudaEvent_t> gemm_ev;// begin/end pairs around every GEMM launch of the last run
+    double last_gemm_seconds = 0.0, last_total_seconds = 0.0;
+    long long last_gemm_launches = 0, last_all_launches = 0;
+    int blocks_per_triple = 0;
+    ~TPlan();
+};
+
+TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode);
+// evaluates triples first, first+stride, ... (< ntriples, at most max_count of them);
+// e_triples_dev (device, ntriples doubles, may be null) receives each triple's weighted
+// contribution at its global index; returns the partial sum in *energy_host.
+void t_plan_run(TPlan &plan, long long first, long long stride, long long max_count, double *e_triples_dev,
+                double *energy_host);
+long long t_count(int o, int mode);
+int t_select_mode(Ctx &ctx, const double *T2, const double *oovv, const double *vovv, const double *ovoo, int o, int v);
+
+void synth_t_inputs(Ctx &ctx, int o, int v, unsigned long long seed, double *T1, double *T2, double *oovv, double *vovv,
+                    double *ovoo, double *eps_o, double *eps_v);
+
+}// namespace qcp2

@@ -40,3 +40,38 @@ def uhf_case(n, nalpha, nbeta, seed):
     Cb, eb = fake_orbitals(n, nbeta, seed + 7)
     no = nalpha + nbeta
     return dict(ao=ao, Ca=Ca, Cb=Cb, eps_a=ea, eps_b=eb, n=n, no=no, nv=2 * n - no)
+
+
+def fock_blocks(eps_a, eps_b, no):
+    """Diagonal spin-orbital Fock blocks as make_moe_tensors builds them (cc.cpp:36-70): alpha on
+    even, beta on odd positions; F_ia is zero (RHF) / the only defined reading for UHF (Q4)."""
+    n2 = 2 * len(eps_a)
+    d = np.empty(n2)
+    d[0::2], d[1::2] = eps_a, eps_b
+    return np.diag(d[:no]).copy(), np.zeros((no, n2 - no)), np.diag(d[no:]).copy()
+
+
+def oracle_pipeline(case, maxiter=100, conv=1e-12, with_t=True):
+    """MP2 -> CCSD -> (T) with the literal C++ oracle on a helpers.rhf_case / uhf_case."""
+    from oracle import oracle as orc
+    uhf = "Ca" in case
+    no, nv = case["no"], case["nv"]
+    if uhf:
+        aa = orc.transform_ao_mo(case["ao"], case["Ca"], case["Ca"])
+        bb = orc.transform_ao_mo(case["ao"], case["Cb"], case["Cb"])
+        ab = orc.transform_ao_mo(case["ao"], case["Ca"], case["Cb"])
+        ea, eb = case["eps_a"], case["eps_b"]
+    else:
+        aa = bb = ab = orc.transform_ao_mo(case["ao"], case["C"], case["C"])
+        ea = eb = case["eps"]
+    so = orc.transform_to_so(aa, bb, ab)
+    F = orc.make_so_moes(ea, eb)
+    I = orc.get_integrals(so, no, nv)
+    T2_mp2, e_mp2 = orc.run_mp2(I["oovv"], orc.make_denom(F, no, nv))
+    foo, fov, fvv = fock_blocks(ea, eb, no)
+    T1, T2, e_cc, iters, hist = orc.ccsd(I, foo, fov, fvv, T2_mp2, maxiter, conv)
+    out = dict(mo_aa=aa, mo_bb=bb, mo_ab=ab, so=so, F=F, ints=I, T2_mp2=T2_mp2, e_mp2=e_mp2, foo=foo, fov=fov, fvv=fvv,
+               T1=T1, T2=T2, e_ccsd=e_cc, iters=iters, e_hist=hist, eps_a=ea, eps_b=eb)
+    if with_t:
+        out["e_t"] = orc.ccsd_t(T1, T2, I["oovv"], I["vovv"], I["ovoo"], foo, fvv)
+    return out

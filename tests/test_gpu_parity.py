@@ -1,0 +1,310 @@
+"""GPU parity tests (run with -m gpu on a B200): every C-ABI entry point against the CPU
+oracles on the same seeded inputs.  Tolerances: energies 1e-10 Eh absolute (the bar of
+BASELINE.json:north_star; observed agreement is ~1e-15), tensors 1e-12 relative to their
+largest element.  All calls go through include/qcp2_b200.h via qc-p2_b200/qcp2.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+from helpers import fock_blocks, oracle_pipeline, rhf_case, uhf_case
+
+import qcp2_b200
+from oracle import np_oracle as npo
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+E_TOL = 1e-10
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "energies.json")))
+
+
+def close(a, b, rel=1e-12):
+    scale = max(1.0, float(np.max(np.abs(b)))) if np.size(b) else 1.0
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) <= rel * scale if np.size(b) else True
+
+
+# ---------------------------------------------------------------------------- GEMM / contract
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (65, 63, 17), (100, 26244 // 4, 33), (38, 1444, 144),
+                                   (400, 1000, 88), (130, 257, 1320), (1, 300, 70), (300, 1, 70), (81, 39, 1521)])
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_dgemm_matches_numpy(ctx, M, N, K, tA, tB):
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((K, M) if tA else (M, K))
+    B = rng.standard_normal((N, K) if tB else (K, N))
+    C0 = rng.standard_normal((M, N))
+    got = ctx.dgemm(tA, tB, 0.75, A, B, -0.5, C0)
+    want = 0.75 * ((A.T if tA else A) @ (B.T if tB else B)) - 0.5 * C0
+    assert np.max(np.abs(got - want)) < 1e-12 * max(1.0, K ** 0.5)
+
+
+def test_dgemm_large_tiles(ctx):
+    rng = np.random.default_rng(1)
+    for (M, N, K) in [(512, 4096, 300), (400, 8192, 1344), (1000, 1000, 1000)]:
+        A, B = rng.standard_normal((M, K)), rng.standard_normal((K, N))
+        got = ctx.dgemm(0, 0, 1.0, A, B, 0.0, np.zeros((M, N)))
+        assert np.max(np.abs(got - A @ B)) < 1e-11 * K ** 0.5
+        got = ctx.dgemm(1, 1, 1.0, np.ascontiguousarray(A.T), np.ascontiguousarray(B.T), 0.0, np.zeros((M, N)))
+        assert np.max(np.abs(got - A @ B)) < 1e-11 * K ** 0.5
+
+
+CONTRACT_PATTERNS = [
+    ("pqrs", "sl", "pqrl"), ("pqrl", "rk", "pqkl"), ("qj", "pqkl", "pjkl"), ("pi", "pjkl", "ijkl"),
+    ("me", "ma", "ae"), ("mf", "mafe", "ae"), ("mnaf", "mnef", "ae"), ("ie", "me", "mi"), ("ne", "mnie", "mi"),
+    ("inef", "mnef", "mi"), ("nf", "mnef", "me"), ("je", "mnie", "mnij"), ("ie", "mnje", "mnij"),
+    ("ijef", "mnef", "mnij"), ("mb", "amef", "abef"), ("ma", "bmef", "abef"), ("mnab", "mnef", "abef"),
+    ("jf", "mbef", "mbej"), ("nb", "mnej", "mbej"), ("jnfb", "mnef", "mbej"), ("jfnb", "mnef", "mbej"),
+    ("ie", "ae", "ia"), ("ma", "mi", "ia"), ("imae", "me", "ia"), ("nf", "naif", "ia"), ("imef", "maef", "ia"),
+    ("mnae", "nmei", "ia"), ("ijae", "be", "ijab"), ("ijbe", "ae", "ijab"), ("mb", "me", "be"),
+    ("imab", "mj", "ijab"), ("jmab", "mi", "ijab"), ("je", "me", "jm"), ("imab", "jm", "ijab"),
+    ("mnab", "mnij", "ijab"), ("ijef", "abef", "ijab"), ("imae", "mbej", "ijab"), ("jmae", "mbei", "ijab"),
+    ("imbe", "maej", "ijab"), ("jmbe", "maei", "ijab"), ("iema", "mbje", "ijab"), ("jemb", "maie", "ijab"),
+    ("ie", "abej", "ijab"), ("je", "abei", "ijab"), ("ma", "mbij", "ijab"), ("mb", "maij", "ijab"),
+    ("jkae", "eibc", "ijkabc"), ("jkce", "eiba", "ijkabc"), ("imbc", "majk", "ijkabc"), ("kmba", "mcji", "ijkabc")]
+
+
+@pytest.mark.parametrize("pattern", CONTRACT_PATTERNS)
+def test_contract_every_reference_pattern(ctx, pattern):
+    """Every distinct index pattern of the reference's 71 btas::contract call sites."""
+    ia, ib, ic = pattern
+    rng = np.random.default_rng(sum(ord(ch) * (q + 1) for q, ch in enumerate(''.join(pattern))))
+    occ, vir = 5, 9
+    ext = {l: (occ if l in "ijkmn" else vir) for l in "abcefijklmnpqrs"}
+    ext.update({l: 6 for l in "pqrsl"})
+    ext["k"] = 6 if "p" in ia + ib + ic else occ
+    ext["j"] = 6 if "p" in ia + ib + ic else occ
+    ext["i"] = 6 if "p" in ia + ib + ic else occ
+    A = rng.standard_normal([ext[l] for l in ia])
+    B = rng.standard_normal([ext[l] for l in ib])
+    C0 = rng.standard_normal([ext[l] for l in ic])
+    got = ctx.contract(0.7, A, ia, B, ib, -0.3, C0, ic)
+    want = -0.3 * C0 + 0.7 * np.einsum(f"{ia},{ib}->{ic}", A, B)
+    assert np.max(np.abs(got - want)) < 1e-12
+    assert np.max(np.abs(got - orc.contract(0.7, A, ia, B, ib, -0.3, C0, ic))) < 1e-12
+
+
+# ---------------------------------------------------------------------------- integrals / mp2
+@pytest.mark.parametrize("n", [1, 2, 7, 24, 33])
+def test_transform_ao_mo(ctx, n):
+    rng = np.random.default_rng(n)
+    ao, C1, C2 = rng.standard_normal((n,) * 4), rng.standard_normal((n, n)), rng.standard_normal((n, n))
+    got = ctx.transform_ao_mo(ao, C1, C2)
+    assert close(got, orc.transform_ao_mo(ao, C1, C2))
+    assert close(got, npo.transform_ao_mo(ao, C1, C2), 1e-11)
+
+
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_transform_to_so_slice_denom(ctx, n):
+    rng = np.random.default_rng(100 + n)
+    aa, bb, ab = (rng.standard_normal((n,) * 4) for _ in range(3))
+    so = ctx.transform_to_so(aa, bb, ab)
+    assert np.array_equal(so, orc.transform_to_so(aa, bb, ab))       # pure gather: bit-exact
+    so_r = ctx.transform_to_so(aa, aa, aa)
+    assert np.array_equal(so_r, orc.transform_to_so(aa, aa, aa))
+    no = 2 * (n // 2) if n > 1 else 2
+    nv = 2 * n - no
+    for spec in qcp2_b200.INT_NAMES + ["vvoo", "vooo"]:
+        assert np.array_equal(ctx.slice_ints(so, no, nv, spec), orc.slice_ints(so, no, nv, spec))
+    ea, eb = np.sort(rng.standard_normal(n)), np.sort(rng.standard_normal(n))
+    F = ctx.make_so_moes(ea, eb)
+    assert np.array_equal(F, orc.make_so_moes(ea, eb))
+    assert np.array_equal(ctx.make_denom(F, no, nv), orc.make_denom(F, no, nv))
+    f1 = ctx.make_fock(ea, eb, 0, no) if no > 0 else None
+    if no > 0 and no % 2 == 0:
+        assert np.array_equal(f1, orc.make_fock(ea, eb, 0, no))
+        assert np.array_equal(ctx.make_fock(ea, eb, no, 2 * n), orc.make_fock(ea, eb, no, 2 * n)) if nv > 0 else True
+
+
+def test_slice_rejects_bad_spec(ctx):
+    with pytest.raises(qcp2_b200.QCP2Error):
+        ctx.slice_ints(np.zeros((4,) * 4), 2, 2, "oxvv")
+
+
+@pytest.mark.parametrize("case_fn", [lambda: rhf_case(6, 2, 31), lambda: uhf_case(5, 3, 2, 32)])
+def test_mp2_driver(ctx, case_fn):
+    case = case_fn()
+    r = oracle_pipeline(case, with_t=False, maxiter=1)
+    uhf = "Ca" in case
+    e, so, T = ctx.MP2(case["ao"], case["Ca"] if uhf else case["C"], case.get("Cb"), r["eps_a"], r["eps_b"],
+                       case["no"], case["nv"], uhf=uhf)
+    assert abs(e - r["e_mp2"]) < E_TOL
+    assert close(so, r["so"]) and close(T, r["T2_mp2"])
+    T_b, e_b = ctx.run_mp2(r["ints"]["oovv"], orc.make_denom(r["F"], case["no"], case["nv"]))
+    assert abs(e_b - r["e_mp2"]) < E_TOL and close(T_b, r["T2_mp2"])
+
+
+# ---------------------------------------------------------------------------- CCSD pieces
+@pytest.fixture(scope="module")
+def cc_state():
+    """Mid-iteration CCSD state (non-zero T1) of an RHF and an as-written UHF pseudo-molecule."""
+    out = {}
+    for name, case in (("rhf", rhf_case(6, 2, 41)), ("uhf", uhf_case(5, 3, 2, 42))):
+        r = oracle_pipeline(case, with_t=False, maxiter=3)
+        out[name] = (case, r)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["rhf", "uhf"])
+def test_elementwise_pieces(ctx, cc_state, kind):
+    case, r = cc_state[kind]
+    assert close(ctx.make_tau(r["T1"], r["T2"]), orc.make_tau(r["T1"], r["T2"]), 1e-15)
+    assert close(ctx.make_tau_bar(r["T1"], r["T2"]), orc.make_tau(r["T1"], r["T2"], True), 1e-15)
+    assert close(ctx.multiply_Ts(r["T1"]), orc.multiply_Ts(r["T1"]), 1e-15)
+    eo, ev = np.diag(r["foo"]), np.diag(r["fvv"])
+    assert np.array_equal(ctx.make_D_ia(r["foo"], r["fvv"]), eo[:, None] - ev[None, :])
+    D2 = ctx.make_D_ijab(r["foo"], r["fvv"])
+    assert np.array_equal(D2, ((eo[:, None, None, None] + eo[None, :, None, None]) - ev[None, None, :, None]) - ev[None, None, None, :])
+    D3 = ctx.make_D_triples(r["foo"], r["fvv"])
+    assert D3.shape == (case["no"],) * 3 + (case["nv"],) * 3
+    i, j, k, a, b, c = 1, 0, 2, 3, 1, 0
+    assert D3[i, j, k, a, b, c] == eo[i] + eo[j] + eo[k] - ev[a] - ev[b] - ev[c]
+
+
+@pytest.mark.parametrize("kind", ["rhf", "uhf"])
+def test_intermediates_T1_T2_energy(ctx, cc_state, kind):
+    case, r = cc_state[kind]
+    I, foo, fov, fvv = r["ints"], r["foo"], r["fov"], r["fvv"]
+    X_ref = orc.update_intermediates(r["T1"], r["T2"], I, foo, fov, fvv)
+    X = ctx.update_intermediates(r["T1"], r["T2"], I, foo, fov, fvv)
+    for k in qcp2_b200.INTER_NAMES:
+        assert close(X[k], X_ref[k]), k
+    X_none = ctx.update_intermediates(r["T1"], r["T2"], I, foo, None, fvv)      # f_ov = NULL means zeros (Q4)
+    for k in qcp2_b200.INTER_NAMES:
+        assert close(X_none[k], X_ref[k]), k
+    fov_r = np.random.default_rng(5).standard_normal(fov.shape) * 0.01           # non-zero F_ia exercises cc.cpp:194,207,223,280,396
+    Xr_ref = orc.update_intermediates(r["T1"], r["T2"], I, foo, fov_r, fvv)
+    Xr = ctx.update_intermediates(r["T1"], r["T2"], I, foo, fov_r, fvv)
+    for k in qcp2_b200.INTER_NAMES:
+        assert close(Xr[k], Xr_ref[k]), k
+    t1_ref = orc.make_T1(r["T1"], r["T2"], I, Xr_ref, foo, fov_r, fvv)
+    assert close(ctx.make_T1(r["T1"], r["T2"], I, Xr_ref, foo, fov_r, fvv), t1_ref)
+    t2_ref = orc.make_T2(t1_ref, r["T2"], I, X_ref, foo, fvv)
+    assert close(ctx.make_T2(t1_ref, r["T2"], I, X_ref, foo, fvv), t2_ref)
+    e_ref = orc.ccsd_energy(r["T1"], r["T2"], I["oovv"], fov_r)
+    assert abs(ctx.ccsd_energy(r["T1"], r["T2"], I["oovv"], fov_r) - e_ref) < 1e-13
+    if kind == "rhf":   # independent einsum formulation of the same equations
+        In = npo.get_integrals(r["so"], case["no"])
+        Xn = npo.intermediates(r["T1"], r["T2"], In, foo, fov, fvv)
+        for k in qcp2_b200.INTER_NAMES:
+            assert close(X[k], Xn[k], 1e-11), k
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_full_pipeline_against_golden(ctx, name):
+    g = GOLDEN[name]
+    spec = g["spec"]
+    case = rhf_case(spec["n"], spec["ndocc"], spec["seed"]) if spec["kind"] == "rhf" else \
+        uhf_case(spec["n"], spec["na"], spec["nb"], spec["seed"])
+    uhf = spec["kind"] == "uhf"
+    no, nv = case["no"], case["nv"]
+    ea, eb = (case["eps_a"], case["eps_b"]) if uhf else (case["eps"], case["eps"])
+    e_mp2, so, T2g = ctx.MP2(case["ao"], case["Ca"] if uhf else case["C"], case.get("Cb"), ea, eb, no, nv, uhf=uhf)
+    assert abs(e_mp2 - g["e_mp2"]) < E_TOL
+    foo, fov, fvv = fock_blocks(ea, eb, no)
+    res = ctx.CCSD(foo, fov, fvv, T2g, 100, 1e-12, so_ints=so, want_sliced=True)
+    assert res["iters"] == g["iters"]
+    assert np.max(np.abs(res["e_hist"] - np.array(g["e_hist"]))) < E_TOL
+    assert abs(res["ccsd_energy"] - g["e_ccsd"]) < E_TOL
+    S = res["sliced_ints"]
+    eo, ev = np.diag(foo).copy(), np.diag(fvv).copy()
+    mode = ctx.t_select_mode(res["T2"], S["oovv"], S["vovv"], S["ovoo"])
+    assert mode == (qcp2_b200.T_LITERAL if uhf else qcp2_b200.T_SYMMETRIC)
+    e_t = ctx.CCSD_T(res["T1"], res["T2"], S["oovv"], S["vovv"], S["ovoo"], eo, ev)
+    assert abs(e_t - g["e_t"]) < E_TOL
+    e_lit = ctx.CCSD_T(res["T1"], res["T2"], S["oovv"], S["vovv"], S["ovoo"], eo, ev, qcp2_b200.T_LITERAL)
+    assert abs(e_lit - g["e_t"]) < E_TOL
+
+
+def test_ccsd_from_presliced_blocks_and_maxiter_cap(ctx):
+    case = rhf_case(6, 2, 51)
+    r = oracle_pipeline(case, with_t=False, maxiter=4)          # stops at the cap, not converged
+    res = ctx.CCSD(r["foo"], r["fov"], r["fvv"], r["T2_mp2"], 4, 1e-12, integrals=r["ints"])
+    assert res["iters"] == r["iters"] == 4
+    assert np.max(np.abs(res["e_hist"] - r["e_hist"])) < E_TOL
+    assert close(res["T2"], r["T2"]) and close(res["T1"], r["T1"])
+
+
+# ---------------------------------------------------------------------------- (T)
+@pytest.mark.parametrize("o,v", [(3, 4), (4, 6), (5, 17), (6, 33)])
+def test_t_synthetic_small_all_modes(ctx, o, v):
+    s = npo.synthetic_t_inputs(o, v)
+    args = (s["T1"], s["T2"], s["oovv"], s["vovv"], s["ovoo"], s["eps_o"], s["eps_v"])
+    ref = orc.ccsd_t(s["T1"], s["T2"], s["oovv"], s["vovv"], s["ovoo"], np.diag(s["eps_o"]), np.diag(s["eps_v"]))
+    for mode in (qcp2_b200.T_LITERAL, qcp2_b200.T_SYMMETRIC, qcp2_b200.T_AUTO):
+        got = ctx.CCSD_T(*args, mode)
+        assert abs(got - ref) < E_TOL and abs(got - ref) < 1e-12 * abs(ref), (mode, got, ref)
+    assert ctx.t_select_mode(s["T2"], s["oovv"], s["vovv"], s["ovoo"]) == qcp2_b200.T_SYMMETRIC
+
+
+def test_t_no_triples_and_unsymmetric_inputs(ctx):
+    s = npo.synthetic_t_inputs(2, 3)
+    args = (s["T1"], s["T2"], s["oovv"], s["vovv"], s["ovoo"], s["eps_o"], s["eps_v"])
+    assert ctx.CCSD_T(*args, qcp2_b200.T_SYMMETRIC) == 0.0           # no i<j<k exists
+    rng = np.random.default_rng(3)
+    o, v = 4, 5
+    T1, T2 = rng.standard_normal((o, v)) * 0.1, rng.standard_normal((o, o, v, v)) * 0.1      # no symmetry at all
+    oovv, vovv, ovoo = (rng.standard_normal(sh) * 0.1 for sh in ((o, o, v, v), (v, o, v, v), (o, v, o, o)))
+    eo, ev = -1.0 - rng.random(o), 1.0 + rng.random(v)
+    assert ctx.t_select_mode(T2, oovv, vovv, ovoo) == qcp2_b200.T_LITERAL
+    ref = orc.ccsd_t(T1, T2, oovv, vovv, ovoo, np.diag(eo), np.diag(ev))
+    assert abs(ctx.CCSD_T(T1, T2, oovv, vovv, ovoo, eo, ev) - ref) < 1e-12 * max(1.0, abs(ref))
+
+
+def test_t_reduced_synthetic_shape_full_sum(ctx):
+    """SURVEY.md section 8d reduced shape o=12, v=96: full E(T) vs the per-triple numpy oracle."""
+    o, v = 12, 96
+    s = npo.synthetic_t_inputs(o, v)
+    args = (s["T1"], s["T2"], s["oovv"], s["vovv"], s["ovoo"], s["eps_o"], s["eps_v"])
+    bu, cu = np.triu_indices(v, 1)
+    trip = npo.sorted_triples(o)
+    per = np.array([npo.ccsd_t_triple_packed_np(*args, int(i), int(j), int(k), bu, cu) for i, j, k in trip])
+    e_tr = np.zeros(len(trip))
+    got = ctx.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, 0, 1, -1, e_tr)
+    assert np.max(np.abs(e_tr - per)) < 1e-12 * np.max(np.abs(per))
+    assert abs(got - per.sum()) < E_TOL
+    # sharding property: strided ranges partition the sum exactly (per-triple values are identical)
+    e2 = np.zeros(len(trip))
+    parts = [ctx.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, r, 3, -1, e2) for r in range(3)]
+    assert np.array_equal(e2, e_tr)
+    assert abs(sum(parts) - got) < 1e-12 * abs(got)
+
+
+def test_t_full_size_sampled_triples_and_device_plan():
+    """Config 5 (o=40, v=400) at full size: sampled triples vs the numpy oracle on identical
+    (device-generated, host-verified) inputs; size-independent properties on the rest."""
+    import torch
+    ctx = qcp2_b200.Context(0)
+    o, v = 40, 400
+    d = qcp2_b200.synth_t_inputs_device(ctx, o, v)
+    host = {k: t.cpu().numpy() for k, t in d.items()}
+    # generator parity: spot-check the device tensors against the numpy generator on slices
+    small = npo.synthetic_t_inputs(6, 9)
+    dsmall = qcp2_b200.synth_t_inputs_device(ctx, 6, 9)
+    for k in small:
+        assert np.array_equal(dsmall[k].cpu().numpy(), small[k]), k
+    plan = qcp2_b200.DeviceTriples(ctx, d["T1"], d["T2"], d["oovv"], d["vovv"], d["ovoo"], d["eps_o"], d["eps_v"],
+                                   qcp2_b200.T_SYMMETRIC)
+    nt = ctx.t_count(o, qcp2_b200.T_SYMMETRIC)
+    assert nt == 9880
+    e_dev = torch.zeros(nt, dtype=torch.float64, device="cuda")
+    trip = npo.sorted_triples(o)
+    bu, cu = np.triu_indices(v, 1)
+    args = tuple(host[k] for k in ("T1", "T2", "oovv", "vovv", "ovoo", "eps_o", "eps_v"))
+    samples = [0, 37, 9879, 4321]          # (0,1,2), (0,1,39), (37,38,39), interior
+    assert tuple(trip[37]) == (0, 1, 39) and tuple(trip[9879]) == (37, 38, 39)
+    for t in samples:
+        plan.run(t, 1, 1, e_dev)
+    got = e_dev.cpu().numpy()
+    for t in samples:
+        i, j, k = map(int, trip[t])
+        ref = npo.ccsd_t_triple_packed_np(*args, i, j, k, bu, cu)
+        assert abs(got[t] - ref) <= 1e-12 * abs(ref), (t, got[t], ref)
+    # a strided batch reproduces the single-triple values bit for bit (batching independence)
+    e2 = torch.zeros(nt, dtype=torch.float64, device="cuda")
+    part = plan.run(0, 4321, 3, e2)   # triples 0, 4321, 8642
+    g2 = e2.cpu().numpy()
+    assert g2[0] == got[0] and g2[4321] == got[4321]
+    assert abs(part - (g2[0] + g2[4321] + g2[8642])) <= 1e-15 * abs(part)
+    tm = plan.timings()
+    assert tm["gemm_launches"] >= 1 and tm["gemm_seconds"] > 0
+    plan.close()
+    ctx.close()

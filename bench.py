@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the post-HF hot path on B200.
+
+Metric (BASELINE.json): (T) FP64 TFLOP/s on the synthetic closed-shell shape o=40, v=400
+(config 5; antisymmetrised counter-based random inputs), counted with the
+ALGORITHMIC flop figure F_T = 2 * v * v(v-1)/2 * 3(v+o) per i<j<k triple, plus CCSD seconds per
+iteration as a secondary object.
+
+A "step" is one batch of `--triples-per-rank` occupied triples per GPU (weak scaling: per-GPU
+work is fixed; 8 GPUs x 5 default steps = the whole 9 880-triple job).  Triples are dealt
+round-robin over ranks; the only exchange is one all-reduce of the per-triple energy vector per
+step.  `value` is timed with the inputs resident in HBM; `e2e` is the whole (T) job through the
+reference-facing C-ABI call with HOST buffers (pinned), host->device copies, NCCL broadcast and
+the final all-reduce inside the timed region.
+
+  python bench.py [--gpus N --steps K --warmup W]           # our arm
+  python bench.py --impl reference [...]                    # the CPU path on the host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ccsd_t_fp64_tflops"
+UNIT = "TFLOP/s"
+
+
+def t_flops_per_triple(o, v):
+    return 2.0 * v * (v * (v - 1) // 2) * 3 * (v + o)
+
+
+def make_config(o, v, world):
+    nt = o * (o - 1) * (o - 2) // 6
+    return {"workload": f"(T) energy, synthetic closed-shell o={o} v={v} (BASELINE.json configs[4]), antisymmetrised "
+                        "counter-based inputs, i<j<k triples dealt round-robin over ranks",
+            "o": o, "v": v, "triples_total": nt, "alg_flops_per_triple": t_flops_per_triple(o, v),
+            "parallelism": f"triples x{world}"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--o", type=int, default=40)
+    ap.add_argument("--v", type=int, default=400)
+    ap.add_argument("--triples-per-rank", type=int, default=247)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ccsd", action="store_true")
+    ap.add_argument("--no-peak", action="store_true", help="skip the cuBLAS FP64 yardstick (profiler runs)")
+    ap.add_argument("--cpu-triples", type=int, default=None, help="triples per CPU sample (default: 3 for cpu_baseline, "
+                    "1 per step for --impl reference)")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# clocks / throttle sampling during the timed region (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), (mx := max(mx, float(r[1])))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU path (the oracle; only cpu_baseline and --impl reference may touch it)
+# ----------------------------------------------------------------------------------------
+CPU_OCC = (0, 1, 2, 20, 39)  # CPU samples draw their triples from these occupied indices
+
+
+class CpuTriples:
+    """Per-triple blocked CPU restatement (numpy/OpenBLAS, all host threads) on sampled i<j<k
+    triples of the same synthetic workload.  Only the tensor slabs those triples read are
+    generated (same counter-based values as the full tensors); generation is not timed."""
+
+    def __init__(self, o, v):
+        from oracle import np_oracle as npo
+        self.npo, self.o, self.v = npo, o, v
+        occ = sorted({min(x, o - 1) for x in CPU_OCC})
+        self.triples = [t for t in npo.sorted_triples(o).tolist() if set(t) <= set(occ)]
+        s = npo.synthetic_t_inputs(o, v, occ=occ)
+        self.args = tuple(s[k] for k in ("T1", "T2", "oovv", "vovv", "ovoo", "eps_o", "eps_v"))
+        self.bu, self.cu = np.triu_indices(v, 1)
+        self.cursor = 0
+
+    def run(self, ntrip):
+        picked, e = [], 0.0
+        t0 = time.perf_counter()
+        for _ in range(ntrip):
+            i, j, k = self.triples[self.cursor % len(self.triples)]
+            self.cursor += 1
+            e += self.npo.ccsd_t_triple_packed_np(*self.args, i, j, k, self.bu, self.cu)
+            picked.append((i, j, k))
+        dt = time.perf_counter() - t0
+        return dt, ntrip * t_flops_per_triple(self.o, self.v), picked, e
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
+        return int(n)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank):
+    args.cpu_triples = args.cpu_triples or 1
+    """--impl reference: the reference's CPU algorithm for this path.  The reference binary
+    cannot be built here (Libint2/BTAS/Eigen absent), so this is the oracle port
+    (oracle/np_oracle.py, per-triple GEMM on OpenBLAS with every host core)."""
+    if rank != 0:
+        return
+    o, v = args.o, args.v
+    cpu = CpuTriples(o, v)
+    for _ in range(min(args.warmup, 1)):  # one warm-up triple is enough to spin up the BLAS threads
+        cpu.run(1)
+    tot_t, flops = 0.0, 0.0
+    for _ in range(args.steps):
+        dt, fl, _, _ = cpu.run(args.cpu_triples)
+        tot_t += dt
+        flops += fl
+    val = flops / tot_t / 1e12
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(make_config(o, v, args.gpus), triples_per_step=args.cpu_triples),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port",
+                             "sample": f"{args.cpu_triples} sampled i<j<k triples per step x {args.steps} steps of the o={o}/v={v} "
+                                       "workload; per-triple M=v,N=v(v-1)/2,K=3(v+o) DGEMM on numpy/OpenBLAS + a<b<c energy sum"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def cublas_fp64_peak(torch, n=8192):
+    """FP64 roofline denominator measured live: cuBLAS DGEMM via torch.matmul (yardstick only)."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty(n, n, dtype=torch.float64, device="cuda")
+
+    def loop(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / iters
+
+    loop(2)
+    burst = min(loop(1) for _ in range(5))
+    sustained = loop(60)  # ~2 s back to back
+    fl = 2.0 * n ** 3
+    del a, b, c
+    return fl / burst / 1e12, fl / sustained / 1e12
+
+
+def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=3):
+    """Secondary metric: CCSD seconds/iteration on the CH4/cc-pVTZ shape (o=10, v=162) with
+    random-init integral blocks (device resident, through the C ABI in device pointer mode)."""
+    import ctypes as C
+    g = torch.Generator(device="cuda").manual_seed(7)
+    f = dict(dtype=torch.float64, device="cuda")
+    ints = [torch.randn(qcp2_b200.int_shape(k, o, v), generator=g, **f) * 0.01 for k in qcp2_b200.INT_NAMES]
+    eo = torch.linspace(-2.0, -0.5, o, **f)
+    ev = torch.linspace(0.5, 3.0, v, **f)
+    foo, fvv, fov = torch.diag(eo).contiguous(), torch.diag(ev).contiguous(), torch.zeros((o, v), **f)
+    D = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
+    guess = (ints[6] / D).contiguous()
+    T1, T2 = torch.empty((o, v), **f), torch.empty((o, o, v, v), **f)
+    E, it = C.c_double(), C.c_int()
+    torch.cuda.synchronize()
+    ctx.set_pointer_mode(qcp2_b200.DEVICE)
+    p = qcp2_b200._p
+    launches0 = ctx.kernel_launches
+    secs = []
+    for rep in range(2):  # first call warms the workspace pool
+        ctx.check(ctx.lib.qcp2_ccsd(ctx.h, None, 0, qcp2_b200._ptrs(ints), p(foo), p(fov), p(fvv), p(guess), o, v, iters,
+                                    C.c_double(0.0), p(T1), p(T2), C.byref(E), C.byref(it), None, None))
+        secs.append(float(ctx.lib.qcp2_ccsd_last_loop_seconds(ctx.h)) / iters)
+    flops = 4.0 * o * o * v ** 4 + 4.0 * o * v ** 4 + 20.0 * o ** 3 * v ** 3 + 4.0 * o ** 4 * v * v + 18.0 * o * o * v ** 3
+    return {"s_per_iter": secs[-1], "o": o, "v": v, "iters_timed": iters, "tflops_reference_formulation": flops / secs[-1] / 1e12,
+            "data": "random-init integral blocks, CH4/cc-pVTZ shape", "launches_per_iter": (ctx.kernel_launches - launches0) // (2 * iters)}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import qcp2_b200
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    o, v, B = args.o, args.v, args.triples_per_rank
+    ctx = qcp2_b200.Context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_pointer_mode(qcp2_b200.DEVICE)
+
+    # ---- inputs: rank 0 generates, NCCL broadcast replicates (outside the timed region for `value`)
+    d = qcp2_b200.synth_t_inputs_device(ctx, o, v)
+    names = ("T1", "T2", "oovv", "vovv", "ovoo", "eps_o", "eps_v")
+    if world > 1:
+        if rank != 0:
+            for k in names:
+                d[k].zero_()
+        qcp2_b200.shard.broadcast_inputs([d[k] for k in names], dist, src=0)
+    plan = qcp2_b200.DeviceTriples(ctx, *(d[k] for k in names), qcp2_b200.T_SYMMETRIC)
+    nt = ctx.t_count(o, qcp2_b200.T_SYMMETRIC)
+    e_trip = torch.zeros(nt, dtype=torch.float64, device="cuda")
+    fpt = t_flops_per_triple(o, v)
+
+    def step(s):
+        first = (s * B * world) % max(nt, 1) + rank
+        e_trip.zero_()
+        plan.run(first, world, B, e_trip)
+        tm = plan.timings()
+        total = qcp2_b200.shard.reduce_triple_energies(e_trip, dist if world > 1 else None)
+        done = len(range(first, nt, world)[:B])
+        return total, tm, done
+
+    for s in range(args.warmup):
+        step(s)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gemm_s, gemm_n, done_local, energy_acc = 0.0, 0, 0, 0.0
+    for s in range(args.steps):
+        total, tm, done = step(args.warmup + s)
+        gemm_s += tm["gemm_seconds"]
+        gemm_n += tm["gemm_launches"]
+        done_local += done
+        energy_acc += total
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = ctx.kernel_launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed = torch.tensor([e0.elapsed_time(e1) * 1e-3, float(done_local), gemm_s, float(gemm_n)], dtype=torch.float64,
+                           device="cuda")
+    if world > 1:
+        mx = elapsed.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = elapsed.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        t_max, done_all = float(mx[0]), float(sm[1])
+    else:
+        t_max, done_all = float(elapsed[0]), float(elapsed[1])
+    value = done_all * fpt / t_max / 1e12
+
+    # ---- roofline of the dominant kernel (the segmented-K DMMA GEMM), this rank
+    peak_burst, peak_sus = (0.0, 0.0) if args.no_peak else cublas_fp64_peak(torch)
+    achieved = done_local * fpt / gemm_s / 1e12 if gemm_s > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
+                "frac": achieved / peak_sus if peak_sus else None, "traffic": None,
+                "kernel": "dgemm_kernel<80x256x16, SEG> (DMMA.8x8x4)", "avg_launch_ms": 1e3 * gemm_s / max(gemm_n, 1),
+                "launches": gemm_n, "alg_flops_per_launch": done_local * fpt / max(gemm_n, 1),
+                "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (sustained ~2 s loop; burst %.2f); "
+                               "MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2" % peak_burst}
+
+    # ---- e2e: the whole (T) job through the C ABI with HOST (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        host = {}
+        if rank == 0:
+            for k in names:
+                h = torch.empty(d[k].shape, dtype=torch.float64, pin_memory=True)
+                h.copy_(d[k])
+                host[k] = h
+        plan.close()
+        del plan
+        h2d = sum(d[k].numel() for k in names) * 8
+        for k in names:
+            d[k] = None
+        torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world == 1:
+            ctx.set_pointer_mode(qcp2_b200.HOST)
+            e_job = ctx.CCSD_T(*(host[k].numpy() for k in names), qcp2_b200.T_AUTO)
+            ctx.set_pointer_mode(qcp2_b200.DEVICE)
+        else:
+            dd = {}
+            for k in names:
+                shape = {"T1": (o, v), "T2": (o, o, v, v), "oovv": (o, o, v, v), "vovv": (v, o, v, v), "ovoo": (o, v, o, o),
+                         "eps_o": (o,), "eps_v": (v,)}[k]
+                dd[k] = torch.empty(shape, dtype=torch.float64, device="cuda")
+                if rank == 0:
+                    dd[k].copy_(host[k], non_blocking=True)
+            qcp2_b200.shard.broadcast_inputs([dd[k] for k in names], dist, src=0)
+            p2 = qcp2_b200.DeviceTriples(ctx, *(dd[k] for k in names), qcp2_b200.T_SYMMETRIC)
+            e_trip.zero_()
+            p2.run(rank, world, -1, e_trip)
+            e_job = qcp2_b200.shard.reduce_triple_energies(e_trip, dist)
+            p2.close()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nt * fpt / float(dt[0]) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d if rank == 0 else 0,
+               "d2h_bytes_per_step": 8 * (nt + 1), "steps": 1, "seconds": float(dt[0]), "e_t": e_job,
+               "what": "whole (T) job (all %d triples) via qcp2_ccsd_t with pinned host buffers" % nt if world == 1 else
+                       "whole (T) job: rank-0 pinned host buffers -> H2D -> NCCL broadcast -> sharded triples -> all-reduce"}
+
+    ccsd = None
+    if rank == 0 and not args.no_ccsd:
+        try:
+            ccsd = ccsd_seconds_per_iter(torch, qcp2_b200, ctx)
+        except Exception as ex:  # never lose the headline line to the secondary metric
+            ccsd = {"error": str(ex)[:200]}
+
+    cpu = None
+    args.cpu_triples = args.cpu_triples or 3
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        dt, fl, pick, _ = CpuTriples(o, v).run(args.cpu_triples)
+        cpu = {"value": fl / dt / 1e12, "unit": UNIT, "cores": host_threads(), "kind": "port",
+               "sample": f"{len(pick)} sampled i<j<k triples {pick} of the same o={o}/v={v} workload, per-triple DGEMM on "
+                         f"numpy/OpenBLAS + a<b<c energy sum, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": dict(make_config(o, v, world), triples_per_rank_per_step=B,
+                               l2="each triple streams 0.84 GB of B rows (>> 126 MB L2); no flush needed"),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "ccsd": ccsd, "energy_checksum": energy_acc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -43,38 +43,49 @@ TAG_T1, TAG_T2, TAG_OOVV, TAG_VOVV, TAG_OVOO = 1, 2, 3, 4, 5
 SEED = 20261019
 
 
-def _antisym_pair_fill(shape, tag, scale, seed, pair):
-    """Dense tensor with values scale*u(tag, linear index of the canonical element) placed on
-    canonical (p<q) positions of the index pair `pair` and extended antisymmetrically."""
-    idx = np.arange(int(np.prod(shape)), dtype=np.uint64).reshape(shape)
-    base = scale * u_rand(seed, tag, idx)
-    p, q = pair
-    ip = np.arange(shape[p]).reshape([-1 if d == p else 1 for d in range(len(shape))])
-    iq = np.arange(shape[q]).reshape([-1 if d == q else 1 for d in range(len(shape))])
-    upper = np.where(ip < iq, base, 0.0)
-    return upper - np.swapaxes(upper, p, q)
+def _sorted_pair(x, y):
+    """(lo, hi, sign) of an index pair: sign +1 if x<y, -1 if x>y, 0 on the diagonal."""
+    return np.minimum(x, y), np.maximum(x, y), np.sign(y - x).astype(np.float64)
 
 
-def synthetic_t_inputs(o, v, seed=SEED):
-    """Antisymmetrised random (T) inputs of SURVEY.md section 8d (config 5 generator)."""
+def _oovv_like_rows(o, v, tag, scale, seed, rows):
+    """Rows `rows` of an [o,o,v,v] tensor antisymmetric in (0,1) and (2,3): value =
+    sign * scale * u(tag, linear index of the canonical i<j, a<b element)."""
+    out = np.zeros((o, o, v, v))
+    j = np.arange(o, dtype=np.int64).reshape(-1, 1, 1)
+    a = np.arange(v, dtype=np.int64).reshape(1, -1, 1)
+    b = np.arange(v, dtype=np.int64).reshape(1, 1, -1)
+    alo, ahi, asg = _sorted_pair(a, b)
+    for i in rows:
+        ilo, ihi, isg = _sorted_pair(np.int64(i), j)
+        idx = ((ilo * o + ihi) * v + alo) * v + ahi
+        out[i] = (isg * asg) * (scale * u_rand(seed, tag, idx.astype(np.uint64)))
+    return out
+
+
+def synthetic_t_inputs(o, v, seed=SEED, occ=None):
+    """Antisymmetrised random (T) inputs of SURVEY.md section 8d (config 5 generator).
+    occ = iterable of occupied indices: only the slabs a triple over those indices reads are
+    generated (T2[occ], oovv[occ], vovv[:, occ]); the rest of the (lazily allocated, zero)
+    full-shape arrays stays untouched, so full-size samples cost a few GB instead of 25."""
+    rows = list(range(o)) if occ is None else sorted(set(int(x) for x in occ))
     T1 = 0.05 * u_rand(seed, TAG_T1, np.arange(o * v, dtype=np.uint64)).reshape(o, v)
-
-    def two_pair(tag, scale):
-        shape = (o, o, v, v)
-        idx = np.arange(o * o * v * v, dtype=np.uint64).reshape(shape)
-        base = scale * u_rand(seed, tag, idx)
-        i = np.arange(o).reshape(-1, 1, 1, 1)
-        j = np.arange(o).reshape(1, -1, 1, 1)
-        a = np.arange(v).reshape(1, 1, -1, 1)
-        b = np.arange(v).reshape(1, 1, 1, -1)
-        c = np.where((i < j) & (a < b), base, 0.0)
-        c = c - c.transpose(1, 0, 2, 3)
-        return c - c.transpose(0, 1, 3, 2)
-
-    T2 = two_pair(TAG_T2, 0.02)
-    oovv = two_pair(TAG_OOVV, 0.1)
-    vovv = _antisym_pair_fill((v, o, v, v), TAG_VOVV, 0.1, seed, (2, 3))
-    ovoo = _antisym_pair_fill((o, v, o, o), TAG_OVOO, 0.1, seed, (2, 3))
+    T2 = _oovv_like_rows(o, v, TAG_T2, 0.02, seed, rows)
+    oovv = _oovv_like_rows(o, v, TAG_OOVV, 0.1, seed, rows)
+    vovv = np.zeros((v, o, v, v))
+    e = np.arange(v, dtype=np.int64).reshape(-1, 1, 1)
+    b = np.arange(v, dtype=np.int64).reshape(1, -1, 1)
+    c = np.arange(v, dtype=np.int64).reshape(1, 1, -1)
+    blo, bhi, bsg = _sorted_pair(b, c)
+    for i in rows:
+        idx = ((e * o + i) * v + blo) * v + bhi
+        vovv[:, i] = bsg * (0.1 * u_rand(seed, TAG_VOVV, idx.astype(np.uint64)))
+    m = np.arange(o, dtype=np.int64).reshape(-1, 1, 1, 1)
+    a = np.arange(v, dtype=np.int64).reshape(1, -1, 1, 1)
+    jj = np.arange(o, dtype=np.int64).reshape(1, 1, -1, 1)
+    kk = np.arange(o, dtype=np.int64).reshape(1, 1, 1, -1)
+    jlo, jhi, jsg = _sorted_pair(jj, kk)
+    ovoo = jsg * (0.1 * u_rand(seed, TAG_OVOO, (((m * v + a) * o + jlo) * o + jhi).astype(np.uint64)))
     eo = -2.0 + 1.5 * np.arange(o) / max(o - 1, 1)
     ev = 0.1 + 2.9 * np.arange(v) / max(v - 1, 1)
     return dict(T1=T1, T2=T2, oovv=oovv, vovv=vovv, ovoo=ovoo, eps_o=eo, eps_v=ev)
@@ -277,9 +288,9 @@ def ccsd_t_triple_packed_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k, bu=None, 
          - np.einsum("a,bc->abc", T1[k], oovv[j, i]))
     V = Y - Y.transpose(1, 0, 2) - Y.transpose(2, 1, 0)
     D = eo[i] + eo[j] + eo[k] - ev[:, None, None] - ev[None, :, None] - ev[None, None, :]
-    a, b, c = np.meshgrid(np.arange(v), np.arange(v), np.arange(v), indexing="ij")
-    m = (a < b) & (b < c)
-    return float(np.sum((W * (W + V) / D)[m]))
+    # W(W+V)/D is totally symmetric in (a,b,c) and vanishes on the diagonals, so the a<b<c sum is
+    # one sixth of the full-cube sum (avoids building index masks)
+    return float(np.sum(W * (W + V) / D)) / 6.0
 
 
 def t_flops(o, v, ntriples=None):

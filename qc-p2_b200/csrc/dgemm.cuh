@@ -103,7 +103,7 @@ struct GemmTile {
     }
 };
 
-template<class Tile, bool A_KC, bool B_NC, int VEC, bool SEG>
+template<class Tile, bool A_KC, bool B_NC, int VEC, bool SEG, int SCHED = 1>
 __global__ void __launch_bounds__(Tile::kThreads, 1) dgemm_kernel(const GemmArgs g) {
     constexpr int BM = Tile::kBM, BN = Tile::kBN, WM = Tile::kWM, WN = Tile::kWN, STAGES = Tile::kStages;
     constexpr int BK = GEMM_BK;
@@ -160,11 +160,14 @@ __global__ void __launch_bounds__(Tile::kThreads, 1) dgemm_kernel(const GemmArgs
         cp_async_commit();
     }
 
+    // SCHED 0: issue the next stage's copies right after the barrier; SCHED 1: after the first
+    // k-step's DMMAs, so the tensor pipe restarts as soon as the first fragments are loaded
+    // and the copy address arithmetic hides behind DMMA issue.
     for (int kb = 0; kb < nkb; ++kb) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            const int nk = kb + STAGES - 1;
+        const int nk = kb + STAGES - 1;
+        if (SCHED == 0) {
             if (nk < nkb) load_stage(nk, nk % STAGES);
             cp_async_commit();
         }
@@ -183,6 +186,10 @@ __global__ void __launch_bounds__(Tile::kThreads, 1) dgemm_kernel(const GemmArgs
             for (int i = 0; i < FM; ++i)
 #pragma unroll
                 for (int j = 0; j < FN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            if (SCHED == 1 && ks == 0) {
+                if (nk < nkb) load_stage(nk, nk % STAGES);
+                cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();
@@ -224,9 +231,9 @@ __global__ void __launch_bounds__(Tile::kThreads, 1) dgemm_kernel(const GemmArgs
 }
 
 // host-side launcher for one instantiation
-template<class Tile, bool A_KC, bool B_NC, int VEC, bool SEG>
+template<class Tile, bool A_KC, bool B_NC, int VEC, bool SEG, int SCHED = 1>
 void launch_dgemm_inst(Ctx &ctx, const GemmArgs &g) {
-    auto kern = dgemm_kernel<Tile, A_KC, B_NC, VEC, SEG>;
+    auto kern = dgemm_kernel<Tile, A_KC, B_NC, VEC, SEG, SCHED>;
     constexpr size_t smem = Tile::template smem_bytes<A_KC, B_NC>();
     static bool configured[64] = {};
     if (!configured[ctx.device & 63]) {
@@ -243,6 +250,7 @@ void launch_dgemm_inst(Ctx &ctx, const GemmArgs &g) {
 using Tile64 = GemmTile<64, 64, 32, 32, 3>;
 using Tile128 = GemmTile<128, 128, 64, 32, 3>;
 using TileT = GemmTile<80, 256, 40, 64, 3>;
+using TileT16 = GemmTile<80, 256, 40, 32, 3>;// 16-warp experiment
 
 // implemented in dgemm_64.cu / dgemm_128.cu / dgemm_t.cu (one translation unit per tile so
 // the instantiations compile in parallel)

@@ -86,8 +86,11 @@ class Context:
             raise QCP2Error(f"qcp2_create(device={device}) failed with status {rc}: a CUDA B200 device is required, "
                             "there is no CPU fallback")
         self.device = device
+        self._children = []  # resident plans; destroyed before the context
 
     def close(self):
+        for child in list(getattr(self, "_children", [])):
+            child.close()
         if getattr(self, "h", None) is not None and self.h:
             self.lib.qcp2_destroy(self.h)
             self.h = None
@@ -334,6 +337,7 @@ class DeviceTriples:
         self.h = C.c_void_p()
         ctx.check(ctx.lib.qcp2_t_plan_create(ctx.h, _p(T1), _p(T2), _p(oovv), _p(vovv), _p(ovoo), _p(eps_o),
                                              _p(eps_v), o, v, mode, C.byref(self.h)))
+        ctx._children.append(self)
 
     def run(self, first=0, stride=1, max_count=-1, e_triples=None):
         E = C.c_double()
@@ -351,6 +355,8 @@ class DeviceTriples:
         if self.h:
             self.ctx.lib.qcp2_t_plan_destroy(self.h)
             self.h = None
+            if self in self.ctx._children:
+                self.ctx._children.remove(self)
 
     def __del__(self):
         try:

@@ -12,8 +12,10 @@
 // requires the physical antisymmetries of T2, <oo||vv>, <vo||vv>, <ov||oo>, packs b<c
 // columns, visits i<j<k and a<b<c only and weights by 36/36.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../../include/qcp2_b200.h"
@@ -56,17 +58,37 @@ struct BuildAArgs {
     const int *ijk;
     double *A;
     int o, v, kpad, count;
+    int tiled, mtiles;// tiled: A[t][m-tile][k-block][TG_BM][TG_ALD] (the TMA kernel's stage image)
     int kb_begin[GEMM_MAX_SEG + 1];
 };
 
 __global__ void build_A_kernel(BuildAArgs p) {
-    const long long per = (long long) p.v * p.kpad, n = per * p.count;
     const long long O = p.o, V = p.v;
+    const int nkb = p.kpad / GEMM_BK;
+    const long long per = p.tiled ? (long long) p.mtiles * nkb * TG_BM * TG_ALD : (long long) p.v * p.kpad;
+    const long long n = per * p.count;
     GRID_STRIDE(lin, n) {
         const int t = (int) (lin / per);
-        const long long rem = lin - (long long) t * per;
-        const long long a = rem / p.kpad;
-        const int col = (int) (rem - a * p.kpad);
+        long long rem = lin - (long long) t * per;
+        long long a;
+        int col;
+        if (p.tiled) {
+            const int c = (int) (rem % TG_ALD);
+            rem /= TG_ALD;
+            const int r = (int) (rem % TG_BM);
+            rem /= TG_BM;
+            const int kb = (int) (rem % nkb);
+            const int mt = (int) (rem / nkb);
+            a = (long long) mt * TG_BM + r;
+            col = kb * GEMM_BK + c;
+            if (c >= GEMM_BK || a >= V) {
+                p.A[lin] = 0.0;
+                continue;
+            }
+        } else {
+            a = rem / p.kpad;
+            col = (int) (rem - a * p.kpad);
+        }
         const int i = p.ijk[3 * t], j = p.ijk[3 * t + 1], k = p.ijk[3 * t + 2];
         int s = 0;
 #pragma unroll
@@ -339,8 +361,17 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     tb = std::max<long long>(1, std::min<long long>(tb, std::min<long long>(4096, std::max<long long>(P->ntriples, 1))));
     P->tb = (int) tb;
     P->blocks_per_triple = v * ((v + kBTile - 1) / kBTile);
+    {
+        const char *env = getenv("QCP2_T_GEMM");// "cpasync" forces the non-TMA kernel (A/B experiments)
+        const bool want_tma = !(env && std::string(env) == "cpasync");
+        const bool rows_aligned = (P->ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(P->vovvP.p) & 15) == 0) &&
+                                  ((reinterpret_cast<uintptr_t>(P->T2P.p) & 15) == 0);
+        P->use_tma = sym && want_tma && rows_aligned;
+        const long long mtiles = (V + TG_BM - 1) / TG_BM;
+        P->a_per_triple = P->use_tma ? mtiles * (P->kpad / GEMM_BK) * TG_BM * TG_ALD : V * P->kpad;
+    }
     for (int s = 0; s < 2; ++s) {
-        P->Abuf[s] = DBuf(ctx, (size_t) (tb * V * P->kpad));
+        P->Abuf[s] = DBuf(ctx, (size_t) (tb * P->a_per_triple));
         P->Xbuf[s] = DBuf(ctx, (size_t) (tb * V * std::max<long long>(P->ncols, 1)));
         P->partial[s] = DBuf(ctx, (size_t) (tb * P->blocks_per_triple));
         QCP2_CUDA(cudaEventCreateWithFlags(&P->gemm_done[s], cudaEventDisableTiming));
@@ -441,22 +472,34 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         BuildAArgs ba;
         ba.T2 = P.T2, ba.ovoo = P.ovoo, ba.ijk = P.ijk_dev + 3 * off, ba.A = P.Abuf[s];
         ba.o = P.o, ba.v = P.v, ba.kpad = P.kpad, ba.count = cnt;
+        ba.tiled = P.use_tma ? 1 : 0, ba.mtiles = (P.v + TG_BM - 1) / TG_BM;
         for (int q = 0; q <= GEMM_MAX_SEG; ++q) ba.kb_begin[q] = P.kb_begin[q];
-        build_A_kernel<<<grid_for((long long) cnt * V * P.kpad, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(ba);
+        build_A_kernel<<<grid_for((long long) cnt * P.a_per_triple, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(ba);
         ctx.launched("build_A");
 
-        GemmArgs g;
-        g.M = P.v, g.N = (int) nc, g.K = P.kpad, g.batch = cnt;
-        g.A = P.Abuf[s], g.lda = P.kpad, g.strideA = V * P.kpad;
-        g.C = P.Xbuf[s], g.ldc = nc, g.strideC = V * nc;
-        g.seg = P.seg_dev + off, g.nseg = GEMM_MAX_SEG, g.seg_aligned = aligned;
-        for (int q = 0; q <= GEMM_MAX_SEG; ++q) g.seg_kb_begin[q] = P.kb_begin[q];
-        for (int q = 0; q < GEMM_MAX_SEG; ++q) {
-            g.seg_rows[q] = q < 3 ? P.v : P.o;
-            g.seg_ldb[q] = sym ? nc : (q < 3 ? O * V * V : V * V);
-        }
         QCP2_CUDA(cudaEventRecord(P.gemm_ev[(size_t) (2 * bq)], ctx.stream));
-        gemm(ctx, g, true, true);
+        if (P.use_tma) {
+            TmaGemmArgs g;
+            g.At = P.Abuf[s], g.strideA = P.a_per_triple;
+            g.C = P.Xbuf[s], g.ldc = nc, g.strideC = V * nc;
+            g.M = P.v, g.N = (int) nc, g.nkb = P.kpad / GEMM_BK;
+            g.seg = P.seg_dev + off, g.nseg = GEMM_MAX_SEG;
+            for (int q = 0; q <= GEMM_MAX_SEG; ++q) g.seg_kb_begin[q] = P.kb_begin[q];
+            for (int q = 0; q < GEMM_MAX_SEG; ++q) g.seg_rows[q] = q < 3 ? P.v : P.o, g.seg_ldb[q] = nc;
+            launch_t_gemm_tma(ctx, g, cnt);
+        } else {
+            GemmArgs g;
+            g.M = P.v, g.N = (int) nc, g.K = P.kpad, g.batch = cnt;
+            g.A = P.Abuf[s], g.lda = P.kpad, g.strideA = V * P.kpad;
+            g.C = P.Xbuf[s], g.ldc = nc, g.strideC = V * nc;
+            g.seg = P.seg_dev + off, g.nseg = GEMM_MAX_SEG, g.seg_aligned = aligned;
+            for (int q = 0; q <= GEMM_MAX_SEG; ++q) g.seg_kb_begin[q] = P.kb_begin[q];
+            for (int q = 0; q < GEMM_MAX_SEG; ++q) {
+                g.seg_rows[q] = q < 3 ? P.v : P.o;
+                g.seg_ldb[q] = sym ? nc : (q < 3 ? O * V * V : V * V);
+            }
+            gemm(ctx, g, true, true);
+        }
         QCP2_CUDA(cudaEventRecord(P.gemm_ev[(size_t) (2 * bq + 1)], ctx.stream));
         ++P.last_gemm_launches;
         QCP2_CUDA(cudaEventRecord(P.gemm_done[s], ctx.stream));

@@ -9,6 +9,22 @@
 
 namespace qcp2 {
 
+// ---- TMA-fed warp-specialised GEMM of the symmetric path (t_gemm_tma.cu) ----
+constexpr int TG_BM = 80, TG_BN = 256, TG_STAGES = 4, TG_ALD = GEMM_BK + 4;
+struct TmaGemmArgs {
+    const double *At = nullptr;  // pre-tiled A: [triple][m-tile][k-block][TG_BM][TG_ALD]
+    long long strideA = 0;       // doubles per triple
+    double *C = nullptr;
+    long long ldc = 0, strideC = 0;
+    int M = 0, N = 0, nkb = 0;
+    const SegDesc *seg = nullptr;
+    int nseg = 0;
+    int seg_kb_begin[GEMM_MAX_SEG + 1] = {0, 0, 0, 0, 0, 0, 0};
+    int seg_rows[GEMM_MAX_SEG] = {0, 0, 0, 0, 0, 0};
+    long long seg_ldb[GEMM_MAX_SEG] = {0, 0, 0, 0, 0, 0};
+};
+void launch_t_gemm_tma(Ctx &ctx, const TmaGemmArgs &g, int batch);
+
 struct TPlan {
     Ctx *ctx = nullptr;
     int o = 0, v = 0, mode = 0;     // mode: QCP2_T_LITERAL or QCP2_T_SYMMETRIC
@@ -33,6 +49,8 @@ struct TPlan {
     double last_gemm_seconds = 0.0, last_total_seconds = 0.0;
     long long last_gemm_launches = 0, last_all_launches = 0;
     int blocks_per_triple = 0;
+    bool use_tma = false;           // symmetric mode with 16-byte aligned packed rows
+    long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
     ~TPlan();
 };
 

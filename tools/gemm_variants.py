@@ -27,7 +27,7 @@ def child():
         tm = plan.timings()
         res.append(dict(gemm_tflops=60 * fpt / tm["gemm_seconds"] / 1e12, total_tflops=60 * fpt / tm["total_seconds"] / 1e12,
                         e=e))
-    print(json.dumps(dict(variant=os.environ.get("QCP2_T_VARIANT", "default"), runs=res)), flush=True)
+    print(json.dumps(dict(variant=os.environ.get("QCP2_T_GEMM", "tma") + ":" + os.environ.get("QCP2_T_VARIANT", "-"), runs=res)), flush=True)
     ctx.close()
 
 
@@ -35,6 +35,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for var in sys.argv[1:] or ["0", "1", "2"]:
-            env = dict(os.environ, QCP2_T_VARIANT=var)
+        for var in sys.argv[1:] or ["tma", "0", "1", "2"]:
+            env = dict(os.environ, QCP2_T_VARIANT=var) if var != "tma" else dict(os.environ)
+            if var != "tma":
+                env["QCP2_T_GEMM"] = "cpasync"
             subprocess.call([sys.executable, os.path.abspath(__file__), "child"], env=env)

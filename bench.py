@@ -247,7 +247,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     o, v, B = args.o, args.v, args.triples_per_rank
     ctx = qcp2_b200.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # one dedicated stream shared by torch (NCCL collectives order against it), the library and
+    # the timing events; torch's default stream has handle 0, which the library reads as "own stream"
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     ctx.set_pointer_mode(qcp2_b200.DEVICE)
 
     # ---- inputs: rank 0 generates, NCCL broadcast replicates (outside the timed region for `value`)

@@ -93,13 +93,15 @@ int qcp2_make_D_triples(qcp2_ctx *ctx, const double *f_oo, const double *f_vv, i
 int qcp2_update_intermediates(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
                               const double *f_oo, const double *f_ov, const double *f_vv, int o, int v,
                               double *const *inter);
-/* make_T1 (cc.cpp:257-292); D_ia is rebuilt from the diagonals of f_oo, f_vv */
+/* make_T1 (cc.cpp:257-292).  D_ia[o,v] is the reference's explicit denominator argument; when it
+ * is NULL the denominators are rebuilt from the diagonals of f_oo, f_vv (make_D_ia). */
 int qcp2_make_T1(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
-                 const double *const *inter, const double *f_oo, const double *f_ov, const double *f_vv, int o, int v,
-                 double *T1_new);
-/* make_T2 (cc.cpp:294-387) */
+                 const double *const *inter, const double *f_oo, const double *f_ov, const double *f_vv,
+                 const double *D_ia, int o, int v, double *T1_new);
+/* make_T2 (cc.cpp:294-387).  Either D_ijab[o,o,v,v] or (f_oo, f_vv) must be given. */
 int qcp2_make_T2(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
-                 const double *const *inter, const double *f_oo, const double *f_vv, int o, int v, double *T2_new);
+                 const double *const *inter, const double *f_oo, const double *f_vv, const double *D_ijab, int o, int v,
+                 double *T2_new);
 /* ccsd_energy (cc.cpp:390-405) */
 int qcp2_ccsd_energy(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *oovv, const double *f_ov, int o,
                      int v, double *energy);

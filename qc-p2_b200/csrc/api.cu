@@ -344,12 +344,14 @@ int qcp2_update_intermediates(qcp2_ctx *ctx, const double *Ts, const double *Td,
 }
 
 int qcp2_make_T1(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
-                 const double *const *inter, const double *f_oo, const double *f_ov, const double *f_vv, int o, int v,
-                 double *T1_new) {
+                 const double *const *inter, const double *f_oo, const double *f_ov, const double *f_vv,
+                 const double *D_ia, int o, int v, double *T1_new) {
     return guarded(ctx, [&](Ctx &c) {
-        QCP2_REQUIRE(Ts && Td && ints && inter && f_oo && f_vv && T1_new, "make_T1: null argument");
+        QCP2_REQUIRE(Ts && Td && ints && inter && T1_new, "make_T1: null argument");
+        QCP2_REQUIRE(D_ia || (f_oo && f_vv), "make_T1: give D_ia or f_oo and f_vv");
         const long long O = o, V = v;
-        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fov(c, f_ov, O * V), fvv(c, f_vv, V * V);
+        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fov(c, f_ov, O * V), fvv(c, f_vv, V * V),
+                dia(c, D_ia, O * V);
         IntsIn I(c, ints, o, v, kNeedT1);
         In xin[X_COUNT];
         InterDev X;
@@ -362,18 +364,21 @@ int qcp2_make_T1(qcp2_ctx *ctx, const double *Ts, const double *Td, const double
             }
         }
         Out t(c, T1_new, O * V);
-        make_T1_dev(c, ts, td, I.dev, X, foo, f_ov ? fov.p : nullptr, fvv, o, v, t);
+        make_T1_dev(c, ts, td, I.dev, X, foo, f_ov ? fov.p : nullptr, fvv, D_ia ? dia.p : nullptr, o, v, t);
         t.finish();
         c.sync();
     });
 }
 
 int qcp2_make_T2(qcp2_ctx *ctx, const double *Ts, const double *Td, const double *const *ints,
-                 const double *const *inter, const double *f_oo, const double *f_vv, int o, int v, double *T2_new) {
+                 const double *const *inter, const double *f_oo, const double *f_vv, const double *D_ijab, int o, int v,
+                 double *T2_new) {
     return guarded(ctx, [&](Ctx &c) {
-        QCP2_REQUIRE(Ts && Td && ints && inter && f_oo && f_vv && T2_new, "make_T2: null argument");
+        QCP2_REQUIRE(Ts && Td && ints && inter && T2_new, "make_T2: null argument");
+        QCP2_REQUIRE(D_ijab || (f_oo && f_vv), "make_T2: give D_ijab or f_oo and f_vv");
         const long long O = o, V = v;
-        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fvv(c, f_vv, V * V);
+        In ts(c, Ts, O * V), td(c, Td, O * O * V * V), foo(c, f_oo, O * O), fvv(c, f_vv, V * V),
+                dd(c, D_ijab, O * O * V * V);
         IntsIn I(c, ints, o, v, kNeedT2);
         In xin[X_COUNT];
         InterDev X;
@@ -383,7 +388,7 @@ int qcp2_make_T2(qcp2_ctx *ctx, const double *Ts, const double *Td, const double
             X.p[k] = const_cast<double *>(xin[k].p);
         }
         Out t(c, T2_new, O * O * V * V);
-        make_T2_dev(c, ts, td, I.dev, X, foo, fvv, o, v, t);
+        make_T2_dev(c, ts, td, I.dev, X, foo, fvv, D_ijab ? dd.p : nullptr, o, v, t);
         t.finish();
         c.sync();
     });

@@ -160,7 +160,7 @@ void update_intermediates_dev(Ctx &ctx, const double *Ts, const double *Td, cons
 
 // cc.cpp:257-292 -- Stanton eq. 1
 void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
-                 const double *fov, const double *fvv, int o, int v, double *T1_new) {
+                 const double *fov, const double *fvv, const double *D_ia, int o, int v, double *T1_new) {
     const long long O = o, V = v;
     const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
     DBuf r(ctx, (size_t) (O * V));
@@ -172,12 +172,13 @@ void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
     contract(ctx, -0.5, td, "imef", int_view(I, I_OVVV, o, v), "maef", 1.0, R, "ia");  // :276
     contract(ctx, -0.5, td, "mnae", int_view(I, I_OOVO, o, v), "nmei", 1.0, R, "ia");  // :277
     if (fov) axpby(ctx, r.p, fov, 1.0, 1.0, O * V);                                    // :280
-    divide_D_ia(ctx, r, foo, fvv, o, v, T1_new);                                       // :283-288
+    if (D_ia) divide_elementwise(ctx, r, D_ia, O * V, T1_new);                         // :283-288
+    else divide_D_ia(ctx, r, foo, fvv, o, v, T1_new);
 }
 
 // cc.cpp:294-387 -- Stanton eq. 2
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
-                 const double *fvv, int o, int v, double *T2_new) {
+                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new) {
     const long long O = o, V = v, o2v2 = O * O * V * V;
     const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
     const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
@@ -217,7 +218,8 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
     contract(ctx, -1.0, ts, "je", vvvo, "abei", 1.0, R, "ijab");        // :367
     contract(ctx, -1.0, ts, "ma", ovoo, "mbij", 1.0, R, "ijab");        // :370
     contract(ctx, 1.0, ts, "mb", ovoo, "maij", 1.0, R, "ijab");         // :371
-    divide_D_ijab(ctx, r, foo, fvv, o, v, T2_new);                      // :374-383
+    if (D_ijab) divide_elementwise(ctx, r, D_ijab, o2v2, T2_new);        // :374-383
+    else divide_D_ijab(ctx, r, foo, fvv, o, v, T2_new);
 }
 
 // cc.cpp:409-451.  Amplitudes, integrals and intermediates never leave the device; the
@@ -247,8 +249,8 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         if (e_hist_host) e_hist_host[it] = e;
         if (std::fabs(de) < conv) break;                                                   // :438 (fabs)
         update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
-        make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, o, v, t1n);                          // :445
-        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, o, v, t2n);                              // :446: new T1, old T2, old X
+        make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);                          // :445
+        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n);                              // :446: new T1, old T2, old X
         QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     }

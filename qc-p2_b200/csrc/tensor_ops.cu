@@ -478,6 +478,15 @@ void divide_D_ijab(Ctx &ctx, const double *r, const double *foo, const double *f
     ctx.launched("D_ijab");
 }
 
+__global__ void divide_kernel(const double *__restrict__ r, const double *__restrict__ D, long long n, double *__restrict__ out) {
+    GRID_STRIDE(i, n) out[i] = r[i] / D[i];
+}
+void divide_elementwise(Ctx &ctx, const double *r, const double *D, long long n, double *out) {
+    if (n <= 0) return;
+    divide_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(r, D, n, out);
+    ctx.launched("divide");
+}
+
 __global__ void diag_kernel(const double *__restrict__ F, int n, double *__restrict__ d) {
     GRID_STRIDE(i, (long long) n) d[i] = F[i * n + i];
 }

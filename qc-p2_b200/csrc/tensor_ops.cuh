@@ -29,6 +29,7 @@ void make_D_ijab(Ctx &ctx, const double *foo, const double *fvv, int o, int v, d
 void make_D_triples(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);
 void divide_D_ia(Ctx &ctx, const double *r, const double *foo, const double *fvv, int o, int v, double *out);
 void divide_D_ijab(Ctx &ctx, const double *r, const double *foo, const double *fvv, int o, int v, double *out);
+void divide_elementwise(Ctx &ctx, const double *r, const double *D, long long n, double *out);
 void ccsd_energy(Ctx &ctx, const double *Ts, const double *Td, const double *oovv, const double *fov, int o, int v,
                  double *e_dev);
 void extract_diag(Ctx &ctx, const double *F, int n, double *d);

@@ -1,0 +1,174 @@
+// cc.cpp -- cc.h entry points on the GPU (reference bodies: cc.cpp:8-560).  The small
+// orbital-energy bookkeeping (make_moe_tensors) stays on the host exactly as written,
+// including the UHF quirks documented in SURVEY.md Q4/Q6.
+#include "cc.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <iostream>
+
+#include "gpu.h"
+
+namespace {
+const char *kNames[11] = {"oooo", "ovoo", "oovo", "ooov", "ovov", "ovvo", "oovv", "vovv", "ovvv", "vvvo", "vvvv"};
+DTensor *field(int_struct &s, int k) {
+    DTensor *f[11] = {&s.oooo, &s.ovoo, &s.oovo, &s.ooov, &s.ovov, &s.ovvo, &s.oovv, &s.vovv, &s.ovvv, &s.vvvo, &s.vvvv};
+    return f[k];
+}
+void int_ptrs(const int_struct &s, const double *p[11]) {
+    const DTensor *f[11] = {&s.oooo, &s.ovoo, &s.oovo, &s.ooov, &s.ovov, &s.ovvo, &s.oovv, &s.vovv, &s.ovvv, &s.vvvo, &s.vvvv};
+    for (int k = 0; k < 11; ++k) p[k] = f[k]->empty() ? nullptr : f[k]->data();
+}
+void inter_ptrs(const cc_intermediates &x, const double *p[6]) {
+    const DTensor *f[6] = {&x.F_ae, &x.F_mi, &x.F_me, &x.W_mnij, &x.W_mbej, &x.W_abef};
+    for (int k = 0; k < 6; ++k) p[k] = f[k]->empty() ? nullptr : f[k]->data();
+}
+// moes.F_ia is left empty on the UHF path (cc.cpp:62-67): NULL = zeros at the ABI
+const double *fov_or_null(const moes &m) { return m.F_ia.empty() ? nullptr : m.F_ia.data(); }
+}// namespace
+
+DTensor make_fock(const Vector &eps1, const Vector &eps2, int n1, int n2) {
+    DTensor result(n2 - n1, n2 - n1);
+    gpu_check(qcp2_make_fock(gpu(), eps1.data(), eps2.data(), n1, n2, result.data()));
+    return result;
+}
+
+moes make_moe_tensors(const scf_results &scf, const params &config) {// cc.cpp:36-70
+    moes result;
+    if (config.ref == "RHF") {
+        result.F = make_fock(scf.moes, scf.moes, 0, scf.no + scf.nv);
+        result.F_ii = make_fock(scf.moes, scf.moes, 0, scf.no);
+        result.F_aa = make_fock(scf.moes, scf.moes, scf.no, scf.no + scf.nv);
+        DTensor F_ia(scf.no, scf.nv);
+        for (int i = 0; i < scf.no; ++i)
+            for (int a = 0; a < scf.nv; ++a) F_ia(i, a) = result.F(i, scf.no + a);
+        result.F_ia = F_ia;
+    }
+    if (config.ref == "UHF") {
+        result.F = make_fock(scf.moes_a, scf.moes_b, 0, scf.no + scf.nv);
+        result.F_ii = make_fock(scf.moes_a, scf.moes_b, 0, scf.no);
+        DTensor F_aa(scf.nv, scf.nv);
+        for (int a = 0; a < scf.nv; ++a) F_aa(a, a) = result.F(scf.no + a, scf.no + a);
+        result.F_aa = F_aa;
+        // cc.cpp:62-67 computes F_ia into a local and drops it: result.F_ia stays empty (Q4)
+    }
+    return result;
+}
+
+DTensor make_D_ia(const moes &m) {
+    const int no = (int) m.F_ii.extent(0), nv = (int) m.F_aa.extent(0);
+    DTensor D(no, nv);
+    gpu_check(qcp2_make_D_ia(gpu(), m.F_ii.data(), m.F_aa.data(), no, nv, D.data()));
+    return D;
+}
+DTensor make_D_ijab(const moes &m) {
+    const int no = (int) m.F_ii.extent(0), nv = (int) m.F_aa.extent(0);
+    DTensor D(no, no, nv, nv);
+    gpu_check(qcp2_make_D_ijab(gpu(), m.F_ii.data(), m.F_aa.data(), no, nv, D.data()));
+    return D;
+}
+DTensor make_D_triples(const moes &m) {
+    const int no = (int) m.F_ii.extent(0), nv = (int) m.F_aa.extent(1);
+    DTensor D(no, no, no, nv, nv, nv);
+    gpu_check(qcp2_make_D_triples(gpu(), m.F_ii.data(), m.F_aa.data(), no, nv, D.data()));
+    return D;
+}
+
+static DTensor tau_like(const DTensor &Ts, const DTensor &Td, int bar) {
+    const int no = (int) Ts.extent(0), nv = (int) Ts.extent(1);
+    DTensor t(no, no, nv, nv);
+    gpu_check(qcp2_make_tau(gpu(), Ts.data(), Td.data(), no, nv, bar, t.data()));
+    return t;
+}
+DTensor make_tau(const DTensor &Ts, const DTensor &Td) { return tau_like(Ts, Td, 0); }
+DTensor make_tau_bar(const DTensor &Ts, const DTensor &Td) { return tau_like(Ts, Td, 1); }
+DTensor multiply_Ts(const DTensor &Ts) {
+    const int no = (int) Ts.extent(0), nv = (int) Ts.extent(1);
+    DTensor r(no, nv, no, nv);
+    gpu_check(qcp2_multiply_Ts(gpu(), Ts.data(), no, nv, r.data()));
+    return r;
+}
+
+cc_intermediates update_intermediates(const DTensor &Ts, const DTensor &Td, const int_struct &integrals, const moes &m) {
+    const int no = (int) Ts.extent(0), nv = (int) Ts.extent(1);
+    cc_intermediates x;
+    x.F_ae = DTensor(nv, nv), x.F_mi = DTensor(no, no), x.F_me = DTensor(no, nv);
+    x.W_mnij = DTensor(no, no, no, no), x.W_mbej = DTensor(no, nv, nv, no), x.W_abef = DTensor(nv, nv, nv, nv);
+    const double *ip[11];
+    int_ptrs(integrals, ip);
+    double *out[6] = {x.F_ae.data(), x.F_mi.data(), x.F_me.data(), x.W_mnij.data(), x.W_mbej.data(), x.W_abef.data()};
+    gpu_check(qcp2_update_intermediates(gpu(), Ts.data(), Td.data(), ip, m.F_ii.data(), fov_or_null(m), m.F_aa.data(), no, nv, out));
+    return x;
+}
+
+DTensor make_T1(const DTensor &Ts, const DTensor &Td, const int_struct &integrals, const cc_intermediates &x,
+                const DTensor &D_ia, const moes &m) {
+    const int no = (int) Ts.extent(0), nv = (int) Ts.extent(1);
+    DTensor t(no, nv);
+    const double *ip[11], *xp[6];
+    int_ptrs(integrals, ip), inter_ptrs(x, xp);
+    gpu_check(qcp2_make_T1(gpu(), Ts.data(), Td.data(), ip, xp, m.F_ii.data(), fov_or_null(m), m.F_aa.data(), D_ia.data(), no, nv, t.data()));
+    return t;
+}
+
+DTensor make_T2(const DTensor &Ts, const DTensor &Td, const int_struct &integrals, const cc_intermediates &x,
+                const DTensor &D_ijab) {
+    const int no = (int) Ts.extent(0), nv = (int) Ts.extent(1);
+    DTensor t(no, no, nv, nv);
+    const double *ip[11], *xp[6];
+    int_ptrs(integrals, ip), inter_ptrs(x, xp);
+    gpu_check(qcp2_make_T2(gpu(), Ts.data(), Td.data(), ip, xp, nullptr, nullptr, D_ijab.data(), no, nv, t.data()));
+    return t;
+}
+
+real_t ccsd_energy(const DTensor &ts, const DTensor &td, const DTensor &oovv, const moes &m) {
+    real_t e = 0.0;
+    gpu_check(qcp2_ccsd_energy(gpu(), ts.data(), td.data(), oovv.data(), fov_or_null(m), (int) ts.extent(0), (int) ts.extent(1), &e));
+    return e;
+}
+
+// cc.cpp:409-451 as ONE device-resident call: integrals are sliced on the GPU (get_integrals,
+// cc.cpp:8-23), amplitudes and intermediates never leave HBM; the host receives the energy of
+// every iteration (what the reference prints) and the final T1/T2 and sliced integrals.
+cc_results CCSD(const scf_results &scf, const mp2_results &mp2, const params &config) {
+    cc_results results;
+    const int o = scf.no, v = scf.nv, n2 = o + v;
+    auto m = make_moe_tensors(scf, config);
+    if (m.F_ii.empty()) throw std::invalid_argument("CCSD: config.ref must be exactly \"RHF\" or \"UHF\" (cc.cpp:39,52)");
+    results.T1 = DTensor(o, v), results.T2 = DTensor(o, o, v, v);
+    double *blocks[11];
+    for (int k = 0; k < 11; ++k) {
+        auto e = [&](char c) { return c == 'o' ? o : v; };
+        *field(results.sliced_ints, k) = DTensor(e(kNames[k][0]), e(kNames[k][1]), e(kNames[k][2]), e(kNames[k][3]));
+        blocks[k] = field(results.sliced_ints, k)->data();
+    }
+    std::vector<double> hist((size_t) std::max(config.maxiter, 1), 0.0);
+    int iters = 0;
+    std::cout << "Starting CCSD Calculations" << std::endl;
+    gpu_check(qcp2_ccsd(gpu(), mp2.so_ints.data(), n2, nullptr, m.F_ii.data(), fov_or_null(m), m.F_aa.data(), mp2.T.data(), o, v,
+                        config.maxiter, config.cc_conv, results.T1.data(), results.T2.data(), &results.ccsd_energy, &iters,
+                        hist.data(), blocks));
+    std::cout << std::endl << "Iter         E_CC (Eh)        Delta(E_CC)" << std::endl;
+    double last = 0.0;
+    for (int it = 0; it <= std::min(iters, config.maxiter - 1); ++it) {
+        printf(" %02d %20.12f %20.12f\n", it, hist[(size_t) it], hist[(size_t) it] - last);
+        last = hist[(size_t) it];
+    }
+    if (iters < config.maxiter) std::cout << "CC energy converged" << std::endl;
+    results.iterations = iters;
+    std::cout << std::endl << "CCSD energy: " << results.ccsd_energy << " Eh" << std::endl;
+    return results;
+}
+
+real_t CCSD_T(const cc_results &cc, const moes &m) {// cc.cpp:454-560
+    const int o = (int) cc.T1.extent(0), v = (int) cc.T1.extent(1);
+    std::vector<double> eo((size_t) o), ev((size_t) v);
+    for (int i = 0; i < o; ++i) eo[(size_t) i] = m.F_ii(i, i);
+    for (int a = 0; a < v; ++a) ev[(size_t) a] = m.F_aa(a, a);
+    real_t e = 0.0;
+    const int_struct &I = cc.sliced_ints;
+    gpu_check(qcp2_ccsd_t(gpu(), cc.T1.data(), cc.T2.data(), I.oovv.data(), I.vovv.data(), I.ovoo.data(), eo.data(), ev.data(), o, v,
+                          QCP2_T_AUTO, &e));
+    std::cout << "(T) energy: " << e << " Eh" << std::endl;
+    return e;
+}

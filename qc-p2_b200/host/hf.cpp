@@ -1,0 +1,233 @@
+// hf.cpp -- Roothaan RHF / UHF on the host, following the reference's src/hf.cpp step by step
+// (guess, Fock build, generalized eigenproblem, density, energy, convergence on |dE| and
+// ||dD||_F, loop from iter = 1 to maxiter-1, no DIIS).  The only deliberate difference: the AO
+// two-electron tensor is computed once and reused for the Fock builds,
+// which changes nothing numerically beyond summation order.
+#include "hf.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <numeric>
+
+bool g_scf_quiet = false;// set by host_api.cpp: suppress the per-iteration table
+
+Matrix density_guess(int nocc, int nao) {
+    Matrix g = Matrix::Zero(nao, nao);
+    for (int i = 0; i < nocc; ++i) g(i, i) = 1.0;
+    return g;
+}
+
+// G_pq = sum_rs D_rs [ 2 (pq|rs) - (pr|qs) ]   with D normalised to N/2 (hf.cpp:223-228)
+Matrix build_fock(const DTensor &ao, const Matrix &D) {
+    const long n = D.rows();
+    Matrix G = Matrix::Zero(n, n);
+#pragma omp parallel for schedule(static)
+    for (long p = 0; p < n; ++p)
+        for (long q = 0; q < n; ++q) {
+            double g = 0.0;
+            for (long r = 0; r < n; ++r)
+                for (long s = 0; s < n; ++s) g += D(r, s) * (2.0 * ao(p, q, r, s) - ao(p, r, q, s));
+            G(p, q) = g;
+        }
+    return G;
+}
+
+// G^sigma_pq = sum_rs [ D_rs (pq|rs) - D^sigma_rs (pr|qs) ]   (hf.cpp:306-311)
+Matrix build_uhf_fock(const DTensor &ao, const Matrix &D, const Matrix &Ds) {
+    const long n = D.rows();
+    Matrix G = Matrix::Zero(n, n);
+#pragma omp parallel for schedule(static)
+    for (long p = 0; p < n; ++p)
+        for (long q = 0; q < n; ++q) {
+            double g = 0.0;
+            for (long r = 0; r < n; ++r)
+                for (long s = 0; s < n; ++s) g += D(r, s) * ao(p, q, r, s) - Ds(r, s) * ao(p, r, q, s);
+            G(p, q) = g;
+        }
+    return G;
+}
+
+real_t rhf_energy(const Matrix &D, const Matrix &H, const Matrix &F) {
+    real_t e = 0.0;
+    for (long i = 0; i < D.rows(); ++i)
+        for (long j = 0; j < D.rows(); ++j) e += D(i, j) * (H(i, j) + F(i, j));
+    return e;
+}
+real_t uhf_energy(const Matrix &D, const Matrix &Da, const Matrix &Db, const Matrix &H, const Matrix &Fa, const Matrix &Fb) {
+    real_t e = 0.0;
+    for (long i = 0; i < D.rows(); ++i)
+        for (long j = 0; j < D.rows(); ++j) e += D(i, j) * H(i, j) + Da(i, j) * Fa(i, j) + Db(i, j) * Fb(i, j);
+    return 0.5 * e;
+}
+
+// cyclic Jacobi for a real symmetric matrix: A = V diag(w) V^T, eigenvalues ascending
+static void jacobi_eigen(Matrix A, Vector &w, Matrix &V) {
+    const long n = A.rows();
+    V = Matrix::Zero(n, n);
+    for (long i = 0; i < n; ++i) V(i, i) = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0;
+        for (long i = 0; i < n; ++i)
+            for (long j = i + 1; j < n; ++j) off += A(i, j) * A(i, j);
+        if (off < 1e-30) break;
+        for (long p = 0; p < n; ++p)
+            for (long q = p + 1; q < n; ++q) {
+                if (std::fabs(A(p, q)) < 1e-300) continue;
+                const double theta = (A(q, q) - A(p, p)) / (2.0 * A(p, q));
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (long k = 0; k < n; ++k) {
+                    const double akp = A(k, p), akq = A(k, q);
+                    A(k, p) = c * akp - s * akq, A(k, q) = s * akp + c * akq;
+                }
+                for (long k = 0; k < n; ++k) {
+                    const double apk = A(p, k), aqk = A(q, k);
+                    A(p, k) = c * apk - s * aqk, A(q, k) = s * apk + c * aqk;
+                }
+                for (long k = 0; k < n; ++k) {
+                    const double vkp = V(k, p), vkq = V(k, q);
+                    V(k, p) = c * vkp - s * vkq, V(k, q) = s * vkp + c * vkq;
+                }
+            }
+    }
+    std::vector<long> order((size_t) n);
+    std::iota(order.begin(), order.end(), 0L);
+    std::sort(order.begin(), order.end(), [&](long a, long b) { return A(a, a) < A(b, b); });
+    w = Vector(n);
+    Matrix Vs(n, n);
+    for (long k = 0; k < n; ++k) {
+        w(k) = A(order[(size_t) k], order[(size_t) k]);
+        for (long i = 0; i < n; ++i) Vs(i, k) = V(i, order[(size_t) k]);
+    }
+    V = Vs;
+}
+
+void generalized_eigen(const Matrix &F, const Matrix &S, Vector &eps, Matrix &C) {
+    const long n = F.rows();
+    Vector s;
+    Matrix U;
+    jacobi_eigen(S, s, U);
+    Matrix X(n, n);// symmetric orthogonalisation S^{-1/2}
+    for (long i = 0; i < n; ++i)
+        for (long j = 0; j < n; ++j) {
+            double x = 0.0;
+            for (long k = 0; k < n; ++k) x += U(i, k) * U(j, k) / std::sqrt(s(k));
+            X(i, j) = x;
+        }
+    Matrix Fp = X.transpose() * F * X, Cp;
+    jacobi_eigen(Fp, eps, Cp);
+    C = X * Cp;
+}
+
+namespace {
+struct OneBody {
+    Matrix S, H;
+};
+OneBody one_body(const std::vector<Atom> &atoms, const BasisSet &obs) {
+    OneBody o;
+    o.S = compute_1body_ints(obs, Operator1::overlap);
+    Matrix T = compute_1body_ints(obs, Operator1::kinetic);
+    Matrix V = compute_1body_ints(obs, Operator1::nuclear, atoms);
+    o.H = T + V;
+    return o;
+}
+}// namespace
+
+scf_results RHF(const std::vector<Atom> &atoms, const BasisSet &obs, real_t nelectron, params config, const DTensor *ao_in) {
+    std::cout << std::endl << "Starting RHF calculation" << std::endl;
+    scf_results results;
+    const double enuc = compute_enuc(atoms);
+    const int ndocc = (int) (nelectron / 2);
+    results.nao = (int) obs.nbf();
+    results.no = (int) (2 * (nelectron / 2));// hf.cpp:355 (nelectron is a real_t there)
+    results.nv = 2 * results.nao - results.no;
+    std::cout << std::endl
+              << "Number of occupied orbitals: " << results.no << std::endl
+              << "Number of virtual orbitals: " << results.nv << std::endl;
+    OneBody ob = one_body(atoms, obs);
+    DTensor own;
+    if (!ao_in) own = eri_ao_tensor(obs), ao_in = &own;
+    // hf.cpp:388-399: the SAD guess is taken only for the exact string "STO-3G"; the shipped
+    // inputs use lower case, so every config goes through density_guess
+    Matrix D = density_guess(ndocc, results.nao);
+    std::cout << std::endl << "Building initial guess" << std::endl;
+    real_t ehf = 0.0;
+    for (int iter = 1; iter < config.maxiter; ++iter) {
+        const real_t ehf_last = ehf;
+        const Matrix D_last = D;
+        Matrix F = ob.H;
+        F += build_fock(*ao_in, D);
+        Vector eps;
+        Matrix C;
+        generalized_eigen(F, ob.S, eps, C);
+        Matrix C_occ = C.leftCols(ndocc);
+        D = C_occ * C_occ.transpose();
+        ehf = rhf_energy(D, ob.H, F);
+        const real_t ediff = ehf - ehf_last, rmsd = (D - D_last).norm();
+        if (iter == 1) std::cout << "\n\n Iter        E(elec)              E(tot)               Delta(E)             RMS(D)\n";
+        if (!g_scf_quiet) printf(" %02d %20.12f %20.12f %20.12f %20.12f\n", iter, ehf, ehf + enuc, ediff, rmsd);
+        results.iterations = iter;
+        if (std::fabs(ediff) < config.scf_conv && std::fabs(rmsd) < config.scf_conv) {
+            results.energy = ehf + enuc;
+            results.D = D, results.F = F, results.C = C, results.moes = eps;
+            results.converged = true;
+            break;
+        }
+    }
+    std::cout << std::endl << "Hartree-Fock Energy = " << results.energy << " Eh" << std::endl;
+    return results;
+}
+
+scf_results UHF(const std::vector<Atom> &atoms, const BasisSet &obs, real_t nelectron, params config, const DTensor *ao_in) {
+    scf_results results;
+    results.nbeta = (int) ((nelectron - config.multiplicity + 1) / 2);
+    results.nalpha = results.nbeta + config.multiplicity - 1;
+    std::cout << std::endl
+              << "Number of alpha electrons: " << results.nalpha << std::endl
+              << "Number of beta electrons: " << results.nbeta << std::endl;
+    results.nao = (int) obs.nbf();
+    results.no = (int) (2 * (nelectron / 2));// = nelectron, also for odd counts
+    results.nv = 2 * results.nao - results.no;
+    std::cout << std::endl
+              << "Number of occupied orbitals: " << results.no << std::endl
+              << "Number of virtual orbitals: " << results.nv << std::endl;
+    std::cout << std::endl << "Starting UHF calculation" << std::endl;
+    const double enuc = compute_enuc(atoms);
+    OneBody ob = one_body(atoms, obs);
+    DTensor own;
+    if (!ao_in) own = eri_ao_tensor(obs), ao_in = &own;
+    Matrix Da = density_guess(results.nalpha, results.nao), Db = density_guess(results.nbeta, results.nao);
+    Matrix D = Da + Db;
+    real_t euhf = 0.0;
+    for (int iter = 1; iter < config.maxiter; ++iter) {
+        const real_t e_last = euhf;
+        const Matrix D_last = D;
+        Matrix Fa = ob.H, Fb = ob.H;
+        Fa += build_uhf_fock(*ao_in, D, Da);
+        Fb += build_uhf_fock(*ao_in, D, Db);
+        Vector ea, eb;
+        Matrix Ca, Cb;
+        generalized_eigen(Fa, ob.S, ea, Ca);
+        generalized_eigen(Fb, ob.S, eb, Cb);
+        Matrix Cao = Ca.leftCols(results.nalpha), Cbo = Cb.leftCols(results.nbeta);
+        Da = Cao * Cao.transpose();
+        Db = Cbo * Cbo.transpose();
+        D = Da + Db;
+        euhf = uhf_energy(D, Da, Db, ob.H, Fa, Fb);
+        const real_t ediff = euhf - e_last, rmsd = (D - D_last).norm();
+        if (iter == 1) std::cout << "\n\n Iter        E(elec)              E(tot)               Delta(E)             RMS(D)\n";
+        if (!g_scf_quiet) printf(" %02d %20.12f %20.12f %20.12f %20.12f\n", iter, euhf, euhf + enuc, ediff, rmsd);
+        results.iterations = iter;
+        if (std::fabs(ediff) < config.scf_conv && std::fabs(rmsd) < config.scf_conv) {
+            results.energy = euhf + enuc;
+            results.D = D, results.Fa = Fa, results.Fb = Fb, results.Ca = Ca, results.Cb = Cb;
+            results.moes_a = ea, results.moes_b = eb;
+            results.converged = true;
+            break;
+        }
+    }
+    std::cout << std::endl << "Hartree-Fock Energy = " << results.energy << " Eh" << std::endl;
+    return results;
+}

@@ -110,7 +110,8 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         """Enqueue device-pointer calls on the given cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream);
-        0/None restores the context's own stream."""
+        0/None restores the context's own stream.  Note torch's *default* stream has handle 0: to
+        share a stream with torch, run under a dedicated `torch.cuda.Stream()` and pass its handle."""
         self.check(self.lib.qcp2_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
     def synchronize(self):
@@ -224,24 +225,24 @@ class Context:
                                                       o, v, _ptrs(outs)))
         return dict(zip(INTER_NAMES, outs))
 
-    def make_T1(self, Ts, Td, integrals, intermediates, f_oo, f_ov, f_vv):
-        ts, td, foo, fov, fvv = _arr(Ts), _arr(Td), _arr(f_oo), _arr(f_ov), _arr(f_vv)
+    def make_T1(self, Ts, Td, integrals, intermediates, f_oo, f_ov, f_vv, D_ia=None):
+        ts, td, foo, fov, fvv, dia = _arr(Ts), _arr(Td), _arr(f_oo), _arr(f_ov), _arr(f_vv), _arr(D_ia)
         o, v = ts.shape
         ints = [_arr(integrals.get(k)) for k in INT_NAMES]
         inter = [_arr(intermediates.get(k)) for k in INTER_NAMES]
         out = np.empty((o, v))
         self.check(self.lib.qcp2_make_T1(self.h, _p(ts), _p(td), _ptrs(ints), _ptrs(inter), _p(foo), _p(fov), _p(fvv),
-                                         o, v, _p(out)))
+                                         _p(dia), o, v, _p(out)))
         return out
 
-    def make_T2(self, Ts, Td, integrals, intermediates, f_oo, f_vv):
-        ts, td, foo, fvv = _arr(Ts), _arr(Td), _arr(f_oo), _arr(f_vv)
+    def make_T2(self, Ts, Td, integrals, intermediates, f_oo=None, f_vv=None, D_ijab=None):
+        ts, td, foo, fvv, dd = _arr(Ts), _arr(Td), _arr(f_oo), _arr(f_vv), _arr(D_ijab)
         o, v = ts.shape
         ints = [_arr(integrals.get(k)) for k in INT_NAMES]
         inter = [_arr(intermediates.get(k)) for k in INTER_NAMES]
         out = np.empty((o, o, v, v))
-        self.check(self.lib.qcp2_make_T2(self.h, _p(ts), _p(td), _ptrs(ints), _ptrs(inter), _p(foo), _p(fvv), o, v,
-                                         _p(out)))
+        self.check(self.lib.qcp2_make_T2(self.h, _p(ts), _p(td), _ptrs(ints), _ptrs(inter), _p(foo), _p(fvv), _p(dd),
+                                         o, v, _p(out)))
         return out
 
     def ccsd_energy(self, ts, td, oovv, f_ov):
@@ -335,11 +336,20 @@ class DeviceTriples:
         self.o, self.v = o, v
         ctx.set_pointer_mode(DEVICE)
         self.h = C.c_void_p()
+        if hasattr(T1, "is_cuda"):
+            import torch
+            torch.cuda.current_stream().synchronize()  # inputs may have been produced on a torch stream
         ctx.check(ctx.lib.qcp2_t_plan_create(ctx.h, _p(T1), _p(T2), _p(oovv), _p(vovv), _p(ovoo), _p(eps_o),
                                              _p(eps_v), o, v, mode, C.byref(self.h)))
         ctx._children.append(self)
 
     def run(self, first=0, stride=1, max_count=-1, e_triples=None):
+        """e_triples: torch CUDA tensor of t_count() doubles (or None).  The caller's torch stream is
+        synchronised first so tensors prepared there (zero_(), broadcast) are complete even when the
+        context runs on its own stream; the call itself returns after the device work is done."""
+        if e_triples is not None and hasattr(e_triples, "is_cuda"):
+            import torch
+            torch.cuda.current_stream().synchronize()
         E = C.c_double()
         self.ctx.check(self.ctx.lib.qcp2_t_plan_run(self.h, C.c_longlong(first), C.c_longlong(stride),
                                                     C.c_longlong(max_count), _p(e_triples), C.byref(E)))

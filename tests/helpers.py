@@ -75,3 +75,23 @@ def oracle_pipeline(case, maxiter=100, conv=1e-12, with_t=True):
     if with_t:
         out["e_t"] = orc.ccsd_t(T1, T2, I["oovv"], I["vovv"], I["ovoo"], foo, fvv)
     return out
+
+
+def load_hostscf():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("qcp2_hostscf", os.path.join(ROOT, "qc-p2_b200", "hostscf.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def molecule_case(xyz, basis, uhf=False, multiplicity=1, conv=1e-12, maxiter=200):
+    """Boundary inputs of a real-molecule config from the host SCF substrate, in the dict
+    layout of rhf_case / uhf_case."""
+    r = load_hostscf().scf(os.path.join(ROOT, "geom", xyz), basis, uhf=uhf, multiplicity=multiplicity, conv=conv,
+                           maxiter=maxiter)
+    if uhf:
+        return dict(ao=r["ao"], Ca=r["Ca"], Cb=r["Cb"], eps_a=r["eps_a"], eps_b=r["eps_b"], n=r["n"], no=r["no"],
+                    nv=r["nv"], e_scf=r["e_scf"], e_nuc=r["e_nuc"])
+    return dict(ao=r["ao"], C=r["Ca"], eps=r["eps_a"], n=r["n"], no=r["no"], nv=r["nv"], e_scf=r["e_scf"],
+                e_nuc=r["e_nuc"])

@@ -13,7 +13,9 @@ def child():
     import torch
     import qcp2_b200
     ctx = qcp2_b200.Context(0)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     ctx.set_pointer_mode(qcp2_b200.DEVICE)
     o, v = 40, 400
     d = qcp2_b200.synth_t_inputs_device(ctx, o, v)

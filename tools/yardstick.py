@@ -45,7 +45,9 @@ def main():
     print("cuBLAS", out["cublas_dgemm"], flush=True)
     ctx = qcp2_b200.Context(0)
     ctx.set_pointer_mode(qcp2_b200.DEVICE)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     rows = []
     shapes = [(8192, 8192, 8192, 0, 0), (8192, 8192, 8192, 0, 1), (8192, 8192, 8192, 1, 0),
               (400, 79800 * 4, 1344, 0, 0), (100, 26244, 26244, 0, 1), (26244, 26244, 100, 1, 0), (4096, 4096, 4096, 0, 0)]

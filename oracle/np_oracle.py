@@ -14,9 +14,12 @@ may import this module.
 """
 import itertools
 
+import functools
+
 import numpy as np
 
 MASK64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_es = functools.partial(np.einsum, optimize=True)  # contractions go through tensordot/BLAS
 
 
 # --------------------------------------------------------------------------------------
@@ -135,7 +138,7 @@ def mp2(oovv, eo, ev):
 # cc.cpp: CCSD (Stanton 1991), written with physicists' einsum
 # --------------------------------------------------------------------------------------
 def _taus(t1, t2):
-    tt = np.einsum("ia,jb->ijab", t1, t1)
+    tt = _es("ia,jb->ijab", t1, t1)
     tt = tt - tt.transpose(0, 1, 3, 2)
     return t2 + tt, t2 + 0.5 * tt
 
@@ -143,24 +146,24 @@ def _taus(t1, t2):
 def intermediates(t1, t2, I, foo, fov, fvv):
     tau, taub = _taus(t1, t2)
     offd = lambda f: f - np.diag(np.diag(f))
-    Fae = offd(fvv) - 0.5 * np.einsum("me,ma->ae", fov, t1) + np.einsum("mf,mafe->ae", t1, I["ovvv"]) \
-        - 0.5 * np.einsum("mnaf,mnef->ae", taub, I["oovv"])
-    Fmi = offd(foo) + 0.5 * np.einsum("ie,me->mi", t1, fov) + np.einsum("ne,mnie->mi", t1, I["ooov"]) \
-        + 0.5 * np.einsum("inef,mnef->mi", taub, I["oovv"])
-    Fme = fov + np.einsum("nf,mnef->me", t1, I["oovv"])
-    Wmnij = I["oooo"] + np.einsum("je,mnie->mnij", t1, I["ooov"]) - np.einsum("ie,mnje->mnij", t1, I["ooov"]) \
-        + 0.25 * np.einsum("ijef,mnef->mnij", tau, I["oovv"])
-    Wabef = I["vvvv"] - np.einsum("mb,amef->abef", t1, I["vovv"]) + np.einsum("ma,bmef->abef", t1, I["vovv"]) \
-        + 0.25 * np.einsum("mnab,mnef->abef", tau, I["oovv"])
-    Wmbej = I["ovvo"] + np.einsum("jf,mbef->mbej", t1, I["ovvv"]) - np.einsum("nb,mnej->mbej", t1, I["oovo"]) \
-        - np.einsum("jnfb,mnef->mbej", 0.5 * t2 + np.einsum("jf,nb->jnfb", t1, t1), I["oovv"])
+    Fae = offd(fvv) - 0.5 * _es("me,ma->ae", fov, t1) + _es("mf,mafe->ae", t1, I["ovvv"]) \
+        - 0.5 * _es("mnaf,mnef->ae", taub, I["oovv"])
+    Fmi = offd(foo) + 0.5 * _es("ie,me->mi", t1, fov) + _es("ne,mnie->mi", t1, I["ooov"]) \
+        + 0.5 * _es("inef,mnef->mi", taub, I["oovv"])
+    Fme = fov + _es("nf,mnef->me", t1, I["oovv"])
+    Wmnij = I["oooo"] + _es("je,mnie->mnij", t1, I["ooov"]) - _es("ie,mnje->mnij", t1, I["ooov"]) \
+        + 0.25 * _es("ijef,mnef->mnij", tau, I["oovv"])
+    Wabef = I["vvvv"] - _es("mb,amef->abef", t1, I["vovv"]) + _es("ma,bmef->abef", t1, I["vovv"]) \
+        + 0.25 * _es("mnab,mnef->abef", tau, I["oovv"])
+    Wmbej = I["ovvo"] + _es("jf,mbef->mbej", t1, I["ovvv"]) - _es("nb,mnej->mbej", t1, I["oovo"]) \
+        - _es("jnfb,mnef->mbej", 0.5 * t2 + _es("jf,nb->jnfb", t1, t1), I["oovv"])
     return dict(F_ae=Fae, F_mi=Fmi, F_me=Fme, W_mnij=Wmnij, W_mbej=Wmbej, W_abef=Wabef)
 
 
 def new_T1(t1, t2, I, X, fov, eo, ev):
-    r = fov + np.einsum("ie,ae->ia", t1, X["F_ae"]) - np.einsum("ma,mi->ia", t1, X["F_mi"]) \
-        + np.einsum("imae,me->ia", t2, X["F_me"]) - np.einsum("nf,naif->ia", t1, I["ovov"]) \
-        - 0.5 * np.einsum("imef,maef->ia", t2, I["ovvv"]) - 0.5 * np.einsum("mnae,nmei->ia", t2, I["oovo"])
+    r = fov + _es("ie,ae->ia", t1, X["F_ae"]) - _es("ma,mi->ia", t1, X["F_mi"]) \
+        + _es("imae,me->ia", t2, X["F_me"]) - _es("nf,naif->ia", t1, I["ovov"]) \
+        - 0.5 * _es("imef,maef->ia", t2, I["ovvv"]) - 0.5 * _es("mnae,nmei->ia", t2, I["oovo"])
     return r / (eo[:, None] - ev[None, :])
 
 
@@ -169,20 +172,20 @@ def new_T2(t1, t2, I, X, eo, ev):
     Pab = lambda x: x - x.transpose(0, 1, 3, 2)
     Pij = lambda x: x - x.transpose(1, 0, 2, 3)
     r = I["oovv"].copy()
-    r += Pab(np.einsum("ijae,be->ijab", t2, X["F_ae"] - 0.5 * np.einsum("mb,me->be", t1, X["F_me"])))
-    r -= Pij(np.einsum("imab,mj->ijab", t2, X["F_mi"] + 0.5 * np.einsum("je,me->mj", t1, X["F_me"])))
-    r += 0.5 * np.einsum("mnab,mnij->ijab", tau, X["W_mnij"])
-    r += 0.5 * np.einsum("ijef,abef->ijab", tau, X["W_abef"])
-    r += Pij(Pab(np.einsum("imae,mbej->ijab", t2, X["W_mbej"])
-                 - np.einsum("ie,ma,mbej->ijab", t1, t1, I["ovvo"])))
-    r += Pij(np.einsum("ie,abej->ijab", t1, I["vvvo"]))
-    r -= Pab(np.einsum("ma,mbij->ijab", t1, I["ovoo"]))
+    r += Pab(_es("ijae,be->ijab", t2, X["F_ae"] - 0.5 * _es("mb,me->be", t1, X["F_me"])))
+    r -= Pij(_es("imab,mj->ijab", t2, X["F_mi"] + 0.5 * _es("je,me->mj", t1, X["F_me"])))
+    r += 0.5 * _es("mnab,mnij->ijab", tau, X["W_mnij"])
+    r += 0.5 * _es("ijef,abef->ijab", tau, X["W_abef"])
+    r += Pij(Pab(_es("imae,mbej->ijab", t2, X["W_mbej"])
+                 - _es("ie,ma,mbej->ijab", t1, t1, I["ovvo"])))
+    r += Pij(_es("ie,abej->ijab", t1, I["vvvo"]))
+    r -= Pab(_es("ma,mbij->ijab", t1, I["ovoo"]))
     D = eo[:, None, None, None] + eo[None, :, None, None] - ev[None, None, :, None] - ev[None, None, None, :]
     return r / D
 
 
 def ccsd_energy(t1, t2, oovv, fov):
-    return np.sum(fov * t1) + 0.25 * np.sum(oovv * t2) + 0.5 * np.einsum("ijab,ia,jb->", oovv, t1, t1)
+    return np.sum(fov * t1) + 0.25 * np.sum(oovv * t2) + 0.5 * _es("ijab,ia,jb->", oovv, t1, t1)
 
 
 def ccsd(I, foo, fov, fvv, t2_guess, maxiter, conv):

@@ -103,7 +103,7 @@ void relayout(Ctx &ctx, double *dst, const double *src, const std::string &from,
 }
 
 void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, double *C, const Spec &s,
-         const Plan &p, int batch, long long sA, long long sB, long long sC) {
+         const Plan &p, int batch, long long sA, long long sB, long long sC, const double *cin) {
     const long long M = prod(p.M, s.c, s.ec), N = prod(p.N, s.c, s.ec), K = prod(p.K, s.a, s.ea);
     QCP2_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "contract: GEMM extent exceeds 2^31");
     DBuf ta, tb, tc;
@@ -134,18 +134,19 @@ void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, 
         Cg = tc.p, sCg = n, g.beta = 0.0;
     } else {
         g.beta = beta;
+        if (cin && beta != 0.0) g.Cin = cin, g.strideCin = sC;// same layout as C
     }
     if (!swapped) {
         g.M = (int) M, g.N = (int) N, g.K = (int) K;
         g.A = Ag, g.lda = a_kc ? K : M, g.strideA = sAg;
         g.B = Bg, g.ldb = b_nc ? N : K, g.strideB = sBg;
-        g.C = Cg, g.ldc = N, g.strideC = sCg;
+        g.C = Cg, g.ldc = N, g.strideC = sCg, g.ldcin = N;
         gemm(ctx, g, a_kc, b_nc);
     } else {// C^T[N][M] = B^T[N][K] . A^T[K][M]
         g.M = (int) N, g.N = (int) M, g.K = (int) K;
         g.A = Bg, g.lda = b_nc ? N : K, g.strideA = sBg;
         g.B = Ag, g.ldb = a_kc ? K : M, g.strideB = sAg;
-        g.C = Cg, g.ldc = M, g.strideC = sCg;
+        g.C = Cg, g.ldc = M, g.strideC = sCg, g.ldcin = M;
         gemm(ctx, g, /*a_kc=*/!b_nc, /*b_nc=*/!a_kc);
     }
     if (!p.c_direct) {
@@ -160,7 +161,7 @@ void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, 
 }// namespace
 
 void contract(Ctx &ctx, double alpha, const TView &A, const char *ia, const TView &B, const char *ib, double beta,
-              const TView &C, const char *ic) {
+              const TView &C, const char *ic, const double *cin) {
     Spec s;
     s.a = ia, s.b = ib, s.c = ic;
     QCP2_REQUIRE((int) s.a.size() == A.rank && (int) s.b.size() == B.rank && (int) s.c.size() == C.rank,
@@ -201,8 +202,13 @@ void contract(Ctx &ctx, double alpha, const TView &A, const char *ia, const TVie
             if (scaled < p0.cost) peel = true;
         }
     }
-    if (peel) run(ctx, alpha, A.p, B.p, beta, C.p, sp, pp, batch, sA, sB, sC);
-    else run(ctx, alpha, A.p, B.p, beta, C.p, s, p0, 1, 0, 0, 0);
+    const Plan &chosen = peel ? pp : p0;
+    if (cin && !chosen.c_direct) {// result goes through a re-layout: seed C with cin first
+        axpby(ctx, C.p, cin, 1.0, 0.0, C.size());
+        cin = nullptr;
+    }
+    if (peel) run(ctx, alpha, A.p, B.p, beta, C.p, sp, pp, batch, sA, sB, sC, cin);
+    else run(ctx, alpha, A.p, B.p, beta, C.p, s, p0, 1, 0, 0, 0, cin);
 }
 
 }// namespace qcp2

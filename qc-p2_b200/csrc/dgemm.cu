@@ -1,9 +1,30 @@
-// dgemm.cu -- alignment analysis and tile selection for the DMMA GEMM.
+// dgemm.cu -- alignment analysis, tile selection and split-K for the DMMA GEMM.
 #include "dgemm.cuh"
 
 namespace qcp2 {
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// sums the split-K partials in split order (deterministic): C = alpha * sum_s P[s] + beta * Cin
+__global__ void splitk_reduce_kernel(const double *__restrict__ P, int splits, long long mn, int N, double *__restrict__ C,
+                                     long long ldc, long long strideC, const double *__restrict__ Cin, long long ldcin,
+                                     long long strideCin, double alpha, double beta, int batch) {
+    const long long total = mn * batch;
+    for (long long lin = (long long) blockIdx.x * blockDim.x + threadIdx.x; lin < total; lin += (long long) gridDim.x * blockDim.x) {
+        const long long z = lin / mn, e = lin - z * mn;
+        const long long row = e / N, col = e - row * N;
+        double s = 0.0;
+        for (int q = 0; q < splits; ++q) s += P[(z * splits + q) * mn + e];
+        s *= alpha;
+        if (beta != 0.0) s += beta * Cin[z * strideCin + row * ldcin + col];
+        C[z * strideC + row * ldc + col] = s;
+    }
+}
+
+struct TileChoice {
+    int bm, bn;
+    double eff;// rough per-CTA tensor-pipe efficiency of the tile shape
+};
 
 void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     QCP2_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "dgemm: negative extent");
@@ -11,8 +32,7 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     // 16-byte cp.async needs every row start to be 16-byte aligned
     bool v2 = aligned16(g.A) && (g.lda % 2 == 0) && (g.strideA % 2 == 0);
     if (g.seg == nullptr) v2 = v2 && aligned16(g.B) && (g.ldb % 2 == 0) && (g.strideB % 2 == 0);
-    else
-    {
+    else {
         v2 = v2 && g.seg_aligned;
         for (int s = 0; s < g.nseg; ++s) v2 = v2 && (g.seg_ldb[s] % 2 == 0);
     }
@@ -22,12 +42,49 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
         launch_dgemm_t(ctx, g, vec, true);
         return;
     }
-    const double work = (double) g.M * (double) g.N * (double) g.batch;
-    // the 128x128 tile pays off once it can fill the machine about twice over
-    const bool big = work >= 2.0 * 128.0 * 128.0 * ctx.sm_count && g.M > 64 && g.N > 64;
-    if (big && a_kc && b_nc && g.M % 80 == 0 && g.M % 128 != 0 && g.N >= 1024) launch_dgemm_t(ctx, g, vec, false);
-    else if (big) launch_dgemm_128(ctx, g, a_kc, b_nc, vec);
-    else launch_dgemm_64(ctx, g, a_kc, b_nc, vec);
+    // tile choice: estimated SM clocks = waves x per-CTA clocks (DMMA-bound: 64 FMA/clk/SM) plus, for
+    // split-K, the bandwidth-bound reduction pass (~3400 B/clk chip-wide) and its launch
+    const TileChoice cand[4] = {{64, 64, 0.70}, {112, 128, 0.88}, {128, 128, 0.90}, {80, 256, 0.90}};
+    const int nkb = (g.K + GEMM_BK - 1) / GEMM_BK;
+    double best = 1e300;
+    int best_t = 0, best_split = 1;
+    for (int t = 0; t < 4; ++t) {
+        if (t == 3 && !(a_kc && b_nc)) continue;// the 80x256 tile is instantiated for [M][K] x [K][N] only
+        const long long tiles = (long long) ((g.M + cand[t].bm - 1) / cand[t].bm) * ((g.N + cand[t].bn - 1) / cand[t].bn) * g.batch;
+        const int cta_per_sm = cand[t].bm == 64 ? 2 : 1;
+        const long long slots = (long long) ctx.sm_count * cta_per_sm;
+        for (int split = 1; split <= 64; split *= 2) {
+            if (split > 1 && (nkb / split < 4 || tiles * (split / 2) >= 4 * slots || t == 3)) break;
+            const long long ctas = tiles * split;
+            const double waves = (double) ((ctas + slots - 1) / slots);
+            const double conc = (double) std::min<long long>(cta_per_sm, (ctas + ctx.sm_count - 1) / ctx.sm_count);
+            const double kb = (double) ((nkb + split - 1) / split) + 6.0;// + prologue/epilogue overhead in k-block units
+            double cost = waves * conc * cand[t].bm * cand[t].bn * kb / (4.0 * cand[t].eff);
+            if (split > 1) cost += 8.0 * g.M * g.N * g.batch * (split + 1) / 3400.0 + 3000.0;
+            if (cost < best) best = cost, best_t = t, best_split = split;
+        }
+    }
+    DBuf ws;
+    GemmArgs run = g;
+    if (best_split > 1) {
+        const long long mn = (long long) g.M * g.N;
+        ws = DBuf(ctx, (size_t) (mn * best_split * g.batch));
+        run.C = ws.p, run.ldc = g.N, run.strideC = mn, run.Cin = nullptr;
+        run.alpha = 1.0, run.beta = 0.0;
+        run.k_splits = best_split, run.kb_per_split = (nkb + best_split - 1) / best_split;
+    }
+    if (best_t == 3) launch_dgemm_t(ctx, run, vec, false);
+    else if (best_t == 2) launch_dgemm_128(ctx, run, a_kc, b_nc, vec);
+    else if (best_t == 1) launch_dgemm_112(ctx, run, a_kc, b_nc, vec);
+    else launch_dgemm_64(ctx, run, a_kc, b_nc, vec);
+    if (best_split > 1) {
+        const long long mn = (long long) g.M * g.N, total = mn * g.batch;
+        const double *cin = g.Cin ? g.Cin : g.C;
+        const long long ldcin = g.Cin ? g.ldcin : g.ldc, scin = g.Cin ? g.strideCin : g.strideC;
+        splitk_reduce_kernel<<<grid_for(total, 256, ctx.sm_count), 256, 0, ctx.stream>>>(ws.p, best_split, mn, g.N, g.C, g.ldc, g.strideC,
+                                                                                      cin, ldcin, scin, g.alpha, g.beta, g.batch);
+        ctx.launched("splitk_reduce");
+    }
 }
 
 }// namespace qcp2

@@ -15,6 +15,8 @@
 // T2[j], T2[k]); each block is padded to a multiple of BK in the K index space and its row
 // pointers are taken from a per-batch descriptor, so nothing is ever copied together.
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace qcp2 {
@@ -38,6 +40,9 @@ struct GemmArgs {
     int M = 0, N = 0, K = 0;
     double alpha = 1.0, beta = 0.0;
     int batch = 1;
+    // split-K: grid.y = k_splits, split s handles k-blocks [s*kb_per_split, ...) and writes its raw
+    // partial product to C + (batch*k_splits + s) * strideC (the launcher points C at a workspace)
+    int k_splits = 1, kb_per_split = 0;
     // SEG mode
     const SegDesc *seg = nullptr;
     int nseg = 0;
@@ -127,19 +132,21 @@ __global__ void __launch_bounds__(Tile::kThreads, 1) dgemm_kernel(const GemmArgs
     const long long bz = blockIdx.z;
     const double *A = g.A + bz * g.strideA;
     const double *B = SEG ? nullptr : g.B + bz * g.strideB;
-    const int nkb = (g.K + BK - 1) / BK;
+    const int nkb_total = (g.K + BK - 1) / BK;
+    const int kb0 = g.k_splits > 1 ? (int) blockIdx.y * g.kb_per_split : 0;
+    const int nkb = g.k_splits > 1 ? max(0, min(nkb_total, kb0 + g.kb_per_split) - kb0) : nkb_total;
 
     auto load_stage = [&](int kb, int stage) {
         double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
-        const int k0 = kb * BK;
+        const int k0 = (kb0 + kb) * BK;
         if (A_KC) load_tile<BM, BK, A_LD, VEC, NT>(as, A, g.lda, m0, k0, g.M, g.K, tid);
         else load_tile<BK, BM, A_LD, VEC, NT>(as, A, g.lda, k0, m0, g.K, g.M, tid);
         if (SEG) {
             int s = 0;
 #pragma unroll
             for (int q = 1; q < GEMM_MAX_SEG; ++q)
-                if (q < g.nseg && kb >= g.seg_kb_begin[q]) s = q;
-            const int lk0 = (kb - g.seg_kb_begin[s]) * BK;
+                if (q < g.nseg && kb0 + kb >= g.seg_kb_begin[q]) s = q;
+            const int lk0 = (kb0 + kb - g.seg_kb_begin[s]) * BK;
             load_tile<BK, BN, B_LD, VEC, NT>(bs, g.seg[bz].B[s], g.seg_ldb[s], lk0, n0, g.seg_rows[s], g.N, tid);
         } else if (B_NC) {
             load_tile<BK, BN, B_LD, VEC, NT>(bs, B, g.ldb, k0, n0, g.K, g.N, tid);
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(Tile::kThreads, 1) dgemm_kernel(const GemmArgs
     cp_async_wait<0>();
 
     // epilogue: C = alpha*acc + beta*Cin
-    double *C = g.C + bz * g.strideC;
+    double *C = g.C + (g.k_splits > 1 ? (bz * g.k_splits + blockIdx.y) : bz) * g.strideC;
     const double *Cin = g.Cin ? g.Cin + bz * g.strideCin : C;
     const long long ldcin = g.Cin ? g.ldcin : g.ldc;
     const bool vec_ok = ((g.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && ((ldcin & 1) == 0) &&
@@ -242,13 +249,14 @@ void launch_dgemm_inst(Ctx &ctx, const GemmArgs &g) {
     }
     const long long tiles = (long long) ((g.M + Tile::kBM - 1) / Tile::kBM) * ((g.N + Tile::kBN - 1) / Tile::kBN);
     QCP2_REQUIRE(tiles > 0 && tiles < (1LL << 31) && g.batch >= 1 && g.batch <= 65535, "dgemm: grid out of range");
-    dim3 grid((unsigned) tiles, 1, (unsigned) g.batch);
+    dim3 grid((unsigned) tiles, (unsigned) std::max(g.k_splits, 1), (unsigned) g.batch);
     kern<<<grid, Tile::kThreads, smem, ctx.stream>>>(g);
     ctx.launched("dgemm");
 }
 
 using Tile64 = GemmTile<64, 64, 32, 32, 3>;
 using Tile128 = GemmTile<128, 128, 64, 32, 3>;
+using Tile112 = GemmTile<112, 128, 56, 32, 3>;// skinny M = o^2 = 100 (particle-particle ladder)
 using TileT = GemmTile<80, 256, 40, 64, 3>;
 using TileT16 = GemmTile<80, 256, 40, 32, 3>;// 16-warp experiment
 
@@ -256,6 +264,7 @@ using TileT16 = GemmTile<80, 256, 40, 32, 3>;// 16-warp experiment
 // the instantiations compile in parallel)
 void launch_dgemm_64(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
 void launch_dgemm_128(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
+void launch_dgemm_112(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
 void launch_dgemm_t(Ctx &ctx, const GemmArgs &g, int vec, bool seg);
 
 // dgemm.cu: alignment analysis + tile choice

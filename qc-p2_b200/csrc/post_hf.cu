@@ -141,21 +141,20 @@ void update_intermediates_dev(Ctx &ctx, const double *Ts, const double *Td, cons
     contract(ctx, 1.0, ts, "nf", oovv, "mnef", 0.0, Fme, "me");                      // :220
     if (fov) axpby(ctx, Fme.p, fov, 1.0, 1.0, O * V);                                // :221-225
 
-    contract(ctx, 1.0, ts, "je", ooov, "mnie", 0.0, Wmnij, "mnij");                  // :229
+    contract(ctx, 1.0, ts, "je", ooov, "mnie", 1.0, Wmnij, "mnij", oooo.p);          // :229 (+ :232 <mn||ij> in the epilogue)
     contract(ctx, -1.0, ts, "ie", ooov, "mnje", 1.0, Wmnij, "mnij");                 // :230
     contract(ctx, 0.25, vtau, "ijef", oovv, "mnef", 1.0, Wmnij, "mnij");             // :231
-    axpby(ctx, Wmnij.p, oooo.p, 1.0, 1.0, O * O * O * O);                            // :232
 
-    contract(ctx, -1.0, ts, "mb", vovv, "amef", 0.0, Wabef, "abef");                 // :237
-    contract(ctx, 1.0, ts, "ma", vovv, "bmef", 1.0, Wabef, "abef");                  // :238
-    contract(ctx, 0.25, vtau, "mnab", oovv, "mnef", 1.0, Wabef, "abef");             // :239
-    axpby(ctx, Wabef.p, I.p[I_VVVV], 1.0, 1.0, V * V * V * V);                       // :240
+    if (Wabef.p) {// the fused solver never materialises W_abef (see make_T2_dev)
+        contract(ctx, -1.0, ts, "mb", vovv, "amef", 1.0, Wabef, "abef", I.p[I_VVVV]);// :237 (+ :240 <ab||ef> in the epilogue)
+        contract(ctx, 1.0, ts, "ma", vovv, "bmef", 1.0, Wabef, "abef");              // :238
+        contract(ctx, 0.25, vtau, "mnab", oovv, "mnef", 1.0, Wabef, "abef");         // :239
+    }
 
-    contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 0.0, Wmbej, "mbej");                  // :245
+    contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 1.0, Wmbej, "mbej", I.p[I_OVVO]);     // :245 (+ :250 <mb||ej> in the epilogue)
     contract(ctx, -1.0, ts, "nb", oovo, "mnej", 1.0, Wmbej, "mbej");                 // :246
     contract(ctx, -0.5, td, "jnfb", oovv, "mnef", 1.0, Wmbej, "mbej");               // :247
     contract(ctx, -1.0, vtt, "jfnb", oovv, "mnef", 1.0, Wmbej, "mbej");              // :249
-    axpby(ctx, Wmbej.p, I.p[I_OVVO], 1.0, 1.0, O * V * V * O);                       // :250
 }
 
 // cc.cpp:257-292 -- Stanton eq. 1
@@ -177,8 +176,13 @@ void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
 }
 
 // cc.cpp:294-387 -- Stanton eq. 2
+// When X.p[X_WABEF] is null the particle-particle ladder 1/2 tau_ijef W_abef is evaluated in
+// factorised form from the integrals (W_abef, v^4 doubles, is never built):
+//   1/2 tau.<ab||ef>  +  1/8 (tau.<mn||ef>).tau_old  -  1/2 P(ab) (tau.<am||ef>).t_old
+// with tau = tau(Ts, Td) and tau_old / t_old the amplitudes the intermediates were built from
+// (Ts_old; cc.cpp:442-446 feeds make_T2 the NEW T1 but OLD intermediates).
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
-                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new) {
+                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new, const double *Ts_old) {
     const long long O = o, V = v, o2v2 = O * O * V * V;
     const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
     const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
@@ -191,8 +195,7 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
     multiply_Ts(ctx, Ts, o, v, tt);
     const TView vtau(tau.p, {O, O, V, V}), vtt(tt.p, {O, V, O, V});
 
-    axpby(ctx, r.p, I.p[I_OOVV], 1.0, 0.0, o2v2);                       // :312
-    contract(ctx, 1.0, td, "ijae", Fae, "be", 1.0, R, "ijab");          // :316
+    contract(ctx, 1.0, td, "ijae", Fae, "be", 1.0, R, "ijab", I.p[I_OOVV]);// :316 (+ :312 <ij||ab> in the epilogue)
     contract(ctx, -1.0, td, "ijbe", Fae, "ae", 1.0, R, "ijab");         // :317
     contract(ctx, 1.0, ts, "mb", Fme, "me", 0.0, D1, "be");             // :322
     contract(ctx, -0.5, td, "ijae", D1, "be", 1.0, R, "ijab");          // :324
@@ -205,7 +208,22 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
     contract(ctx, 1.0, ts, "ie", Fme, "me", 0.0, D2, "im");             // :341-342
     contract(ctx, 0.5, td, "jmab", D2, "im", 1.0, R, "ijab");           // :343
     contract(ctx, 0.5, vtau, "mnab", Wmnij, "mnij", 1.0, R, "ijab");    // :346
-    contract(ctx, 0.5, vtau, "ijef", Wabef, "abef", 1.0, R, "ijab");    // :348  particle-particle ladder
+    if (Wabef.p) {
+        contract(ctx, 0.5, vtau, "ijef", Wabef, "abef", 1.0, R, "ijab");// :348  particle-particle ladder
+    } else {
+        QCP2_REQUIRE(Ts_old != nullptr, "make_T2: factorised ladder needs the amplitudes the intermediates were built from");
+        const TView to(Ts_old, {O, V}), vvvv = int_view(I, I_VVVV, o, v), vovv = int_view(I, I_VOVV, o, v),
+                    oovv = int_view(I, I_OOVV, o, v);
+        DBuf tau_old(ctx, (size_t) o2v2), y(ctx, (size_t) (O * O * O * O)), z(ctx, (size_t) (O * O * V * O));
+        make_tau(ctx, Ts_old, Td, o, v, false, tau_old);
+        const TView vtauo(tau_old.p, {O, O, V, V}), Y(y.p, {O, O, O, O}), Z(z.p, {O, O, V, O});
+        contract(ctx, 0.5, vtau, "ijef", vvvv, "abef", 1.0, R, "ijab");   // 1/2 tau <ab||ef>          (cc.cpp:240 in :348)
+        contract(ctx, 1.0, vtau, "ijef", oovv, "mnef", 0.0, Y, "ijmn");   // 1/8 tau <mn||ef> tau_old  (cc.cpp:239 in :348)
+        contract(ctx, 0.125, Y, "ijmn", vtauo, "mnab", 1.0, R, "ijab");
+        contract(ctx, 1.0, vtau, "ijef", vovv, "amef", 0.0, Z, "ijam");   // -1/2 P(ab) tau <am||ef> t (cc.cpp:237-238 in :348)
+        contract(ctx, -0.5, Z, "ijam", to, "mb", 1.0, R, "ijab");
+        contract(ctx, 0.5, Z, "ijbm", to, "ma", 1.0, R, "ijab");
+    }
     contract(ctx, 1.0, td, "imae", Wmbej, "mbej", 1.0, R, "ijab");      // :354  ring terms
     contract(ctx, -1.0, td, "jmae", Wmbej, "mbei", 1.0, R, "ijab");     // :355
     contract(ctx, -1.0, td, "imbe", Wmbej, "maej", 1.0, R, "ijab");     // :356
@@ -230,7 +248,11 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     const long long O = o, V = v, o2v2 = O * O * V * V;
     DBuf xbuf[X_COUNT];
     InterDev X;
-    for (int k = 0; k < X_COUNT; ++k) xbuf[k] = DBuf(ctx, (size_t) inter_block_size(k, o, v)), X.p[k] = xbuf[k].p;
+    for (int k = 0; k < X_COUNT; ++k) {
+        X.p[k] = nullptr;
+        if (k == X_WABEF) continue;// factorised ladder: the v^4 intermediate is never allocated
+        xbuf[k] = DBuf(ctx, (size_t) inter_block_size(k, o, v)), X.p[k] = xbuf[k].p;
+    }
     DBuf t1n(ctx, (size_t) (O * V)), t2n(ctx, (size_t) o2v2), e_dev(ctx, 1);
     fill_zero(ctx, T1, O * V);                                                             // :417-419
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
@@ -250,7 +272,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         if (std::fabs(de) < conv) break;                                                   // :438 (fabs)
         update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
         make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);                          // :445
-        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n);                              // :446: new T1, old T2, old X
+        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1);                              // :446: new T1, old T2, old X
         QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     }

@@ -28,7 +28,8 @@ void update_intermediates_dev(Ctx &ctx, const double *Ts, const double *Td, cons
 void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
                  const double *fov, const double *fvv, const double *D_ia, int o, int v, double *T1_new);
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
-                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new);
+                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new,
+                 const double *Ts_old = nullptr);
 void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,
               const double *T2_guess, int o, int v, int maxiter, double conv, double *T1, double *T2, double *e_host,
               int *iters_host, double *e_hist_host);

@@ -188,6 +188,86 @@ __global__ void __launch_bounds__(kBlock) t_energy_kernel(EnergyArgs p) {
     }
 }
 
+// Symmetric-mode energy sweep, tiled.  For fixed a the three X terms of
+//   W[a,b,c] = X[a,p(b,c)] - X[b,p(a,c)] + X[c,p(a,b)]          (a < b < c)
+// are the packed row a plus M_a - M_a^T of the square matrix M_a[r][s] = X[r, p(a,s)] (r,s > a),
+// whose rows are contiguous.  One block (4 warps) owns one work item (a, bt <= ct): a 32x32 tile
+// pair of M_a.  The (b,c) tile of M_a and of row a is read straight from global memory, the (c,b)
+// tile is transposed through shared memory -- every element of X is fetched exactly once, with
+// coalesced requests.  Column data (three <oo||vv> values, three T1 values, eps_c) live in
+// registers, row data in shared memory; all offsets inside one X slice are 32-bit.  Work items are
+// enumerated on the host, so no empty blocks are launched.
+constexpr int kEBlock = 128;
+struct EnergySymArgs {
+    const double *X, *T1, *oovvP, *eo, *ev;
+    const int *ijk;
+    const int *items;// [n_items][3] = (a, bt, ct)
+    double *partial;
+    int o, v;
+    long long np;
+};
+
+__global__ void __launch_bounds__(kEBlock) t_energy_sym_kernel(EnergySymArgs p) {
+    __shared__ double Mt[32][33];
+    __shared__ double qb[3][32], tbs[3][32], evb[32];
+    __shared__ double ws[kEBlock / 32];
+    const int t = blockIdx.y;
+    const int a = p.items[3 * blockIdx.x], bt = p.items[3 * blockIdx.x + 1], ct = p.items[3 * blockIdx.x + 2];
+    const int s0 = a + 1, v = p.v;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long V = p.v, O = p.o, np = p.np;
+    const int i = p.ijk[3 * t], j = p.ijk[3 * t + 1], k = p.ijk[3 * t + 2];
+    const double *X = p.X + (long long) t * V * np;
+    const double *O0 = p.oovvP + (j * O + k) * np, *O1 = p.oovvP + (i * O + k) * np, *O2 = p.oovvP + (j * O + i) * np;
+    const int inp = (int) np;
+    const int pa = (int) pair_index(a, s0, V) - s0;// p(a, s) = pa + s
+    const int b0 = s0 + bt * 32, c0 = s0 + ct * 32, c = c0 + tx;
+    const bool c_ok = c < v;
+#pragma unroll
+    for (int rr = ty; rr < 32; rr += kEBlock / 32) {// M_a[c rows][b cols], transposed on read-out
+        const int row = c0 + rr, col = b0 + tx;
+        Mt[rr][tx] = (row < v && col < v) ? X[row * inp + pa + col] : 0.0;
+    }
+    if (threadIdx.x < 96) {
+        const int w = threadIdx.x >> 5;
+        const double *Owp = w == 0 ? O0 : (w == 1 ? O1 : O2);
+        const long long ow = w == 0 ? i : (w == 1 ? j : k);
+        const bool ok = b0 + tx < v;
+        qb[w][tx] = ok ? Owp[pa + b0 + tx] : 0.0;
+        tbs[w][tx] = ok ? p.T1[ow * V + b0 + tx] : 0.0;
+    } else {
+        evb[tx] = (b0 + tx < v) ? p.ev[b0 + tx] : 0.0;
+    }
+    const double qc0 = c_ok ? O0[pa + c] : 0.0, qc1 = c_ok ? O1[pa + c] : 0.0, qc2 = c_ok ? O2[pa + c] : 0.0;
+    const double tc0 = c_ok ? p.T1[i * V + c] : 0.0, tc1 = c_ok ? p.T1[j * V + c] : 0.0, tc2 = c_ok ? p.T1[k * V + c] : 0.0;
+    const double tia = p.T1[i * V + a], tja = p.T1[j * V + a], tka = p.T1[k * V + a];
+    const double dac = p.eo[i] + p.eo[j] + p.eo[k] - p.ev[a] - (c_ok ? p.ev[c] : 0.0);
+    const double *Xa = X + (long long) a * np;
+    __syncthreads();
+    double sum = 0.0;
+#pragma unroll
+    for (int r = ty; r < 32; r += kEBlock / 32) {
+        const int b = b0 + r;
+        if (b < c && c_ok) {
+            const int pbc = b * v - ((b * (b + 1)) >> 1) + (c - b - 1);
+            const double W = Xa[pbc] - X[b * inp + pa + c] + Mt[tx][r];
+            const double Ya = tia * O0[pbc] - tja * O1[pbc] - tka * O2[pbc];
+            const double Yb = tbs[0][r] * qc0 - tbs[1][r] * qc1 - tbs[2][r] * qc2;
+            const double Yc = tc0 * qb[0][r] - tc1 * qb[1][r] - tc2 * qb[2][r];
+            sum += W * (W + (Ya - Yb + Yc)) / (dac - evb[r]);
+        }
+    }
+    sum = warp_sum(sum);
+    if (tx == 0) ws[ty] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kEBlock / 32; ++w) s += ws[w];
+        p.partial[(long long) t * gridDim.x + blockIdx.x] = s;
+    }
+}
+
 // one block per triple: fixed-order sum of the block partials -> weighted triple energy
 __global__ void t_finish_kernel(const double *__restrict__ partial, int bpt, double weight, double *__restrict__ e_run,
                                 double *__restrict__ e_triples, const long long *__restrict__ gidx) {
@@ -319,6 +399,7 @@ TPlan::~TPlan() {
     for (cudaEvent_t e : gemm_ev) cudaEventDestroy(e);
     if (seg_dev) cudaFree(seg_dev);
     if (ijk_dev) cudaFree(ijk_dev);
+    if (items_dev) cudaFree(items_dev);
     if (aux) cudaStreamDestroy(aux);
 }
 
@@ -360,7 +441,23 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     tb = std::min(tb, std::max<long long>(1, (4LL << 30) / xbytes));
     tb = std::max<long long>(1, std::min<long long>(tb, std::min<long long>(4096, std::max<long long>(P->ntriples, 1))));
     P->tb = (int) tb;
-    P->blocks_per_triple = v * ((v + kBTile - 1) / kBTile);
+    {
+        if (sym) {// work items (a, bt <= ct) of the tiled energy sweep
+            QCP2_REQUIRE(V * P->ncols < (1LL << 31), "(T): v * v(v-1)/2 must stay below 2^31");
+            std::vector<int> items;
+            for (int a = 0; a + 2 < v; ++a) {
+                const int nt = (v - a - 1 + 31) / 32;
+                for (int ct = 0; ct < nt; ++ct)
+                    for (int bt = 0; bt <= ct; ++bt) items.push_back(a), items.push_back(bt), items.push_back(ct);
+            }
+            P->sym_items = (int) (items.size() / 3);
+            if (P->sym_items > 0) {
+                QCP2_CUDA(cudaMalloc(&P->items_dev, items.size() * sizeof(int)));
+                QCP2_CUDA(cudaMemcpy(P->items_dev, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
+        P->blocks_per_triple = sym ? std::max(P->sym_items, 1) : v * ((v + kBTile - 1) / kBTile);
+    }
     {
         const char *env = getenv("QCP2_T_GEMM");// "cpasync" forces the non-TMA kernel (A/B experiments)
         const bool want_tma = !(env && std::string(env) == "cpasync");
@@ -505,13 +602,30 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         QCP2_CUDA(cudaEventRecord(P.gemm_done[s], ctx.stream));
 
         QCP2_CUDA(cudaStreamWaitEvent(P.aux, P.gemm_done[s], 0));
+        static const bool skip_energy = getenv("QCP2_T_SKIP_ENERGY") != nullptr;// experiments only: GEMM-alone timing
+        if (skip_energy) {
+            QCP2_CUDA(cudaEventRecord(P.energy_done[s], P.aux));
+            continue;
+        }
         EnergyArgs ea;
         ea.X = P.Xbuf[s], ea.T1 = P.T1, ea.oovv = sym ? P.oovvP.p : P.oovv, ea.eo = P.eo, ea.ev = P.ev;
         ea.ijk = P.ijk_dev + 3 * off, ea.partial = P.partial[s];
         ea.o = P.o, ea.v = P.v, ea.nbt = (P.v + kBTile - 1) / kBTile, ea.ncols = nc;
-        dim3 grid((unsigned) P.blocks_per_triple, 1, (unsigned) cnt);
-        if (sym) t_energy_kernel<true><<<grid, kBlock, 0, P.aux>>>(ea);
-        else t_energy_kernel<false><<<grid, kBlock, 0, P.aux>>>(ea);
+        if (sym) {
+            EnergySymArgs es;
+            es.X = P.Xbuf[s], es.T1 = P.T1, es.oovvP = P.oovvP.p, es.eo = P.eo, es.ev = P.ev;
+            es.ijk = P.ijk_dev + 3 * off, es.partial = P.partial[s], es.o = P.o, es.v = P.v, es.np = nc;
+            es.items = P.items_dev;
+            if (P.sym_items > 0) {
+                dim3 grid((unsigned) P.sym_items, (unsigned) cnt, 1);
+                t_energy_sym_kernel<<<grid, kEBlock, 0, P.aux>>>(es);
+            } else {
+                QCP2_CUDA(cudaMemsetAsync(P.partial[s].p, 0, (size_t) cnt * sizeof(double), P.aux));
+            }
+        } else {
+            dim3 grid((unsigned) (P.v * ((P.v + kBTile - 1) / kBTile)), 1, (unsigned) cnt);
+            t_energy_kernel<false><<<grid, kBlock, 0, P.aux>>>(ea);
+        }
         ctx.launched("t_energy");
         t_finish_kernel<<<cnt, kBlock, 0, P.aux>>>(P.partial[s], P.blocks_per_triple, weight, e_run.p + off, e_triples_dev,
                                                   gidx_dev + off);

@@ -49,6 +49,8 @@ struct TPlan {
     double last_gemm_seconds = 0.0, last_total_seconds = 0.0;
     long long last_gemm_launches = 0, last_all_launches = 0;
     int blocks_per_triple = 0;
+    int sym_items = 0;              // work items (a, bt <= ct) of the symmetric energy sweep
+    int *items_dev = nullptr;
     bool use_tma = false;           // symmetric mode with 16-byte aligned packed rows
     long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
     ~TPlan();

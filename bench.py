@@ -202,7 +202,7 @@ def cublas_fp64_peak(torch, n=8192):
     return fl / burst / 1e12, fl / sustained / 1e12
 
 
-def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=3):
+def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=3, cpu_sample=False):
     """Secondary metric: CCSD seconds/iteration on the CH4/cc-pVTZ shape (o=10, v=162) with
     random-init integral blocks (device resident, through the C ABI in device pointer mode)."""
     import ctypes as C
@@ -226,8 +226,21 @@ def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=3):
                                     C.c_double(0.0), p(T1), p(T2), C.byref(E), C.byref(it), None, None))
         secs.append(float(ctx.lib.qcp2_ccsd_last_loop_seconds(ctx.h)) / iters)
     flops = 4.0 * o * o * v ** 4 + 4.0 * o * v ** 4 + 20.0 * o ** 3 * v ** 3 + 4.0 * o ** 4 * v * v + 18.0 * o * o * v ** 3
-    return {"s_per_iter": secs[-1], "o": o, "v": v, "iters_timed": iters, "tflops_reference_formulation": flops / secs[-1] / 1e12,
-            "data": "random-init integral blocks, CH4/cc-pVTZ shape", "launches_per_iter": (ctx.kernel_launches - launches0) // (2 * iters)}
+    out = {"s_per_iter": secs[-1], "o": o, "v": v, "iters_timed": iters, "tflops_reference_formulation": flops / secs[-1] / 1e12,
+           "data": "random-init integral blocks, CH4/cc-pVTZ shape", "launches_per_iter": (ctx.kernel_launches - launches0) // (2 * iters)}
+    if cpu_sample:
+        # one iteration of the numpy/einsum CPU port (BLAS on all host cores) on the same blocks
+        from oracle import np_oracle as npo
+        I = {k: t.cpu().numpy() for k, t in zip(qcp2_b200.INT_NAMES, ints)}
+        foo_h, fov_h, fvv_h, t2_h = foo.cpu().numpy(), fov.cpu().numpy(), fvv.cpu().numpy(), guess.cpu().numpy()
+        t1_h = np.zeros((o, v))
+        t0 = time.perf_counter()
+        X = npo.intermediates(t1_h, t2_h, I, foo_h, fov_h, fvv_h)
+        t1n = npo.new_T1(t1_h, t2_h, I, X, fov_h, eo.cpu().numpy(), ev.cpu().numpy())
+        npo.new_T2(t1n, t2_h, I, X, eo.cpu().numpy(), ev.cpu().numpy())
+        out["cpu_s_per_iter"] = time.perf_counter() - t0
+        out["cpu_kind"] = "port (oracle/np_oracle.py, einsum->OpenBLAS), %d threads, 1 iteration" % host_threads()
+    return out
 
 
 def main():
@@ -315,9 +328,15 @@ def main():
     # ---- roofline of the dominant kernel (the segmented-K DMMA GEMM), this rank
     peak_burst, peak_sus = (0.0, 0.0) if args.no_peak else cublas_fp64_peak(torch)
     achieved = done_local * fpt / gemm_s / 1e12 if gemm_s > 0 else 0.0
+    # DRAM bytes per triple of the GEMM from the committed ncu --set full capture
+    # (profiles/r1_t_gemm_tma_ncu_full.txt: 2.745 GB read + 0.751 GB written for a 3-triple launch);
+    # algorithmic bytes per triple: B rows 843 MB + X 255 MB + A 5 MB = 1.10 GB
+    dram_per_triple = (2.744980e9 + 0.750871e9) / 3.0 if (o, v) == (40, 400) else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
-                "frac": achieved / peak_sus if peak_sus else None, "traffic": None,
-                "kernel": "dgemm_kernel<80x256x16, SEG> (DMMA.8x8x4)", "avg_launch_ms": 1e3 * gemm_s / max(gemm_n, 1),
+                "frac": achieved / peak_sus if peak_sus else None,
+                "traffic": dram_per_triple * done_local / max(gemm_n, 1) if dram_per_triple else None,
+                "kernel": "t_gemm_tma_kernel (80x256x16 CTA tile, 4-stage cp.async.bulk/mbarrier ring, 8 DMMA.8x8x4 consumer warps)",
+                "avg_launch_ms": 1e3 * gemm_s / max(gemm_n, 1),
                 "launches": gemm_n, "alg_flops_per_launch": done_local * fpt / max(gemm_n, 1),
                 "peak_source": "cuBLAS DGEMM 8192^3 via torch.matmul measured in this run (sustained ~2 s loop; burst %.2f); "
                                "MEASURED_PEAKS.json has no FP64 entry; nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2" % peak_burst}
@@ -371,7 +390,7 @@ def main():
     ccsd = None
     if rank == 0 and not args.no_ccsd:
         try:
-            ccsd = ccsd_seconds_per_iter(torch, qcp2_b200, ctx)
+            ccsd = ccsd_seconds_per_iter(torch, qcp2_b200, ctx, cpu_sample=(world == 1 and not args.no_cpu_baseline))
         except Exception as ex:  # never lose the headline line to the secondary metric
             ccsd = {"error": str(ex)[:200]}
 

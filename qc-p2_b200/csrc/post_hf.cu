@@ -41,42 +41,31 @@ static TView int_view(const IntsDev &I, int k, int o, int v) {
 }
 
 // ---------------------------------------------------------------------------------
-// integrals.cpp:95-134 -- four quarter transformations, 2 n^5 flop each, as four GEMM
-// launches (two of them batched) without any re-layout:
-//   X1[(pqr), l]    = sum_s ao[(pqr), s]   C1[s, l]                      (:121)
-//   X2[(pq)][k][l]  = sum_r C1[r, k]       X1[(pq)][r][l]   batch n^2    (:123)
-//   X3[p][j][(kl)]  = sum_q C2[q, j]       X2[p][q][(kl)]   batch n      (:126)
-//   out[i][(jkl)]   = sum_p C2[p, i]       X3[p][(jkl)]                  (:129)
+// integrals.cpp:95-134 -- four quarter transformations, 2 n^5 flop each.  Every step contracts
+// the LAST index of the current tensor with a coefficient matrix and puts the new index FIRST:
+//   Z1[l,p,q,r] = sum_s C1[s,l] (pq|rs)      (:121)        one dense GEMM each:
+//   Z2[k,l,p,q] = sum_r C1[r,k] Z1[l,p,q,r]  (:123)        out[n][n^3] = C^T[n][n] . in^T[n][n^3]
+//   Z3[j,k,l,p] = sum_q C2[q,j] Z2[k,l,p,q]  (:126)        (A = C as [K][M], B = in as [N][K])
+//   out[i,j,k,l] = sum_p C2[p,i] Z3[j,k,l,p] (:129)
+// after four rotations the indices are back in (ij|kl) order -- no batching, no re-layout.
 // ---------------------------------------------------------------------------------
 void transform_ao_mo_dev(Ctx &ctx, const double *ao, const double *C1, const double *C2, int n, double *out) {
-    QCP2_REQUIRE(n >= 1 && n <= 255, "transform_ao_mo: n out of range (1..255)");
-    const long long n2 = (long long) n * n, n3 = n2 * n, n4 = n3 * n;
+    QCP2_REQUIRE(n >= 1 && n <= 1024, "transform_ao_mo: n out of range");
+    const long long n3 = (long long) n * n * n, n4 = n3 * n;
+    QCP2_REQUIRE(n3 < (1LL << 31), "transform_ao_mo: n^3 exceeds 2^31");
     DBuf x1(ctx, (size_t) n4), x2(ctx, (size_t) n4);
-    GemmArgs g;
-    g.M = (int) n3, g.N = n, g.K = n;
-    g.A = ao, g.lda = n, g.B = C1, g.ldb = n, g.C = x1, g.ldc = n;
-    gemm(ctx, g, true, true);
-
-    g = GemmArgs();
-    g.M = n, g.N = n, g.K = n, g.batch = (int) n2;
-    g.A = C1, g.lda = n, g.strideA = 0;      // [K=r][M=k]
-    g.B = x1, g.ldb = n, g.strideB = n2;     // [K=r][N=l]
-    g.C = x2, g.ldc = n, g.strideC = n2;
-    gemm(ctx, g, false, true);
-
-    g = GemmArgs();
-    g.M = n, g.N = (int) n2, g.K = n, g.batch = n;
-    g.A = C2, g.lda = n, g.strideA = 0;      // [K=q][M=j]
-    g.B = x2, g.ldb = n2, g.strideB = n3;    // [K=q][N=(kl)]
-    g.C = x1, g.ldc = n2, g.strideC = n3;    // x1 reused as X3
-    gemm(ctx, g, false, true);
-
-    g = GemmArgs();
-    g.M = n, g.N = (int) n3, g.K = n;
-    g.A = C2, g.lda = n;                     // [K=p][M=i]
-    g.B = x1, g.ldb = n3;                    // [K=p][N=(jkl)]
-    g.C = out, g.ldc = n3;
-    gemm(ctx, g, false, true);
+    auto rotate = [&](const double *in, const double *Cm, double *res) {
+        GemmArgs g;
+        g.M = n, g.N = (int) n3, g.K = n;
+        g.A = Cm, g.lda = n;   // [K][M]
+        g.B = in, g.ldb = n;   // [N][K]
+        g.C = res, g.ldc = n3;
+        gemm(ctx, g, false, false);
+    };
+    rotate(ao, C1, x1);
+    rotate(x1, C1, x2);
+    rotate(x2, C2, x1);
+    rotate(x1, C2, out);
 }
 
 // mp2.cpp:45-86 from the AO integrals on.

@@ -164,53 +164,43 @@ void fill_zero(Ctx &ctx, double *p, long long n) {
     if (n > 0) QCP2_CUDA(cudaMemsetAsync(p, 0, (size_t) n * sizeof(double), ctx.stream));
 }
 
-// integrals.cpp:136-167 as a gather: one thread per <ij||kl>, l fastest.
+// integrals.cpp:136-167 as a gather.  One block per (i,j) row pair, threads sweep (k,l) with l
+// fastest: writes are fully coalesced, reads walk rows of the spatial tensors (each value
+// serves two l's), all index arithmetic is 32-bit.
 __global__ void to_so_kernel(const double *__restrict__ aa, const double *__restrict__ bb,
                              const double *__restrict__ ab, int n, double *__restrict__ so) {
-    const long long n2 = 2LL * n, total = n2 * n2 * n2 * n2;
-    GRID_STRIDE(lin, total) {
-        long long r = lin;
-        const int l = (int) (r % n2);
-        r /= n2;
-        const int k = (int) (r % n2);
-        r /= n2;
-        const int j = (int) (r % n2);
-        const int i = (int) (r / n2);
-        const int si = i & 1, sj = j & 1, sk = k & 1, sl = l & 1;
-        const long long I = i >> 1, J = j >> 1, K = k >> 1, L = l >> 1;
-        const long long ikjl = ((I * n + K) * n + J) * n + L, jkil = ((J * n + K) * n + I) * n + L;
+    const int n2 = 2 * n;
+    const int i = blockIdx.x / n2, j = blockIdx.x - i * n2;
+    const int si = i & 1, sj = j & 1, I = i >> 1, J = j >> 1;
+    double *out = so + (size_t) blockIdx.x * n2 * n2;
+    const size_t n3 = (size_t) n * n * n, nn = (size_t) n * n;
+    const double *same = si ? bb : aa;
+    for (int kl = threadIdx.x; kl < n2 * n2; kl += blockDim.x) {
+        const int k = kl / n2, l = kl - k * n2;
+        const int sk = k & 1, sl = l & 1, K = k >> 1, L = l >> 1;
+        const size_t ikjl = I * n3 + K * nn + (size_t) J * n + L, jkil = J * n3 + K * nn + (size_t) I * n + L;
         double val = 0.0;
-        if (si == sk && sj == sl) {
-            if (si == sj) {
-                const double *m = si ? bb : aa;
-                val = m[ikjl] - m[jkil];// :143-149
-            } else
-                val = ab[ikjl];// :151-155
-        } else if (si == sl && sj == sk && si != sj) {
-            val = -ab[jkil];// :157-161
-        }
-        so[lin] = val;// the remaining spin patterns are the zero-initialised ones
+        if (si == sk && sj == sl) val = (si == sj) ? same[ikjl] - same[jkil] : ab[ikjl];// :143-155
+        else if (si == sl && sj == sk && si != sj) val = -ab[jkil];                    // :157-161
+        out[kl] = val;// the remaining spin patterns are the zero-initialised ones
     }
 }
 void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, double *so) {
-    const long long total = 16LL * n * n * n * n;
-    if (total == 0) return;
-    to_so_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(aa, bb, ab, n, so);
+    if (n <= 0) return;
+    to_so_kernel<<<4u * n * n, kBlock, 0, ctx.stream>>>(aa, bb, ab, n, so);
     ctx.launched("to_so");
 }
 
-__global__ void slice_kernel(const double *__restrict__ so, long long n2, int e0, int e1, int e2, int e3, int m0,
-                             int m1, int m2, int m3, double *__restrict__ out) {
-    const long long total = (long long) e0 * e1 * e2 * e3;
-    GRID_STRIDE(lin, total) {
-        long long r = lin;
-        const int s = (int) (r % e3);
-        r /= e3;
-        const int q3 = (int) (r % e2);
-        r /= e2;
-        const int q2 = (int) (r % e1);
-        const int p = (int) (r / e1);
-        out[lin] = so[(((p + m0) * n2 + (q2 + m1)) * n2 + (q3 + m2)) * n2 + (s + m3)];
+// integrals.cpp:184-207.  One block per (p,q) pair of the block's first two indices; threads copy
+// the contiguous-in-s rows of the (r,s) panel.
+__global__ void slice_kernel(const double *__restrict__ so, int n2, int e1, int e2, int e3, int m0, int m1, int m2, int m3,
+                             double *__restrict__ out) {
+    const int p = blockIdx.x / e1, q = blockIdx.x - p * e1;
+    const double *src = so + ((size_t) (p + m0) * n2 + (q + m1)) * n2 * n2 + (size_t) m2 * n2 + m3;
+    double *dst = out + (size_t) blockIdx.x * e2 * e3;
+    for (int rs = threadIdx.x; rs < e2 * e3; rs += blockDim.x) {
+        const int r = rs / e3, s = rs - r * e3;
+        dst[rs] = src[r * n2 + s];
     }
 }
 void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *spec, double *out) {
@@ -224,8 +214,7 @@ void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *s
     QCP2_REQUIRE(o + v <= n2, "slice_ints: o + v exceeds the spin-orbital count");
     const long long total = (long long) e[0] * e[1] * e[2] * e[3];
     if (total == 0) return;
-    slice_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(so, n2, e[0], e[1], e[2], e[3],
-                                                                                 m[0], m[1], m[2], m[3], out);
+    slice_kernel<<<(unsigned) (e[0] * e[1]), kBlock, 0, ctx.stream>>>(so, n2, e[1], e[2], e[3], m[0], m[1], m[2], m[3], out);
     ctx.launched("slice");
 }
 

@@ -25,7 +25,8 @@ def close(a, b, rel=1e-12):
 
 # ---------------------------------------------------------------------------- GEMM / contract
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (65, 63, 17), (100, 26244 // 4, 33), (38, 1444, 144),
-                                   (400, 1000, 88), (130, 257, 1320), (1, 300, 70), (300, 1, 70), (81, 39, 1521)])
+                                   (400, 1000, 88), (130, 257, 1320), (1, 300, 70), (300, 1, 70), (81, 39, 1521),
+                                   (100, 2000, 5000), (10, 162, 40000), (162, 162, 16200), (3, 5, 70000)])  # split-K / 112-row tile shapes
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_dgemm_matches_numpy(ctx, M, N, K, tA, tB):
     rng = np.random.default_rng(M * 7 + N * 3 + K)
@@ -35,6 +36,16 @@ def test_dgemm_matches_numpy(ctx, M, N, K, tA, tB):
     got = ctx.dgemm(tA, tB, 0.75, A, B, -0.5, C0)
     want = 0.75 * ((A.T if tA else A) @ (B.T if tB else B)) - 0.5 * C0
     assert np.max(np.abs(got - want)) < 1e-12 * max(1.0, K ** 0.5)
+
+
+def test_contract_with_large_contracted_dimension_uses_split_k(ctx):
+    """T1-residual pattern cc.cpp:276 at a size where the output is 10 x 60 and K = 10*60*60."""
+    rng = np.random.default_rng(11)
+    o, v = 10, 60
+    td, ovvv = rng.standard_normal((o, o, v, v)), rng.standard_normal((o, v, v, v))
+    got = ctx.contract(-0.5, td, "imef", ovvv, "maef", 0.0, np.zeros((o, v)), "ia")
+    want = -0.5 * np.einsum("imef,maef->ia", td, ovvv)
+    assert np.max(np.abs(got - want)) < 1e-10
 
 
 def test_dgemm_large_tiles(ctx):

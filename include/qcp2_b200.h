@@ -149,6 +149,16 @@ int qcp2_t_plan_timings(const qcp2_t_plan *plan, double *gemm_seconds, double *t
                         long long *all_launches);
 int qcp2_t_plan_destroy(qcp2_t_plan *plan);
 
+/* Fused pipeline main.cpp:76-88 runs after the SCF: MP2 -> CCSD -> (T) with every tensor resident
+ * on the device between the stages (the stepwise entry points above each return host tensors, as
+ * the reference's functions do: so_ints is 7 GB at CH4/cc-pVTZ).  Inputs are the hot-path boundary
+ * data of qcp2_mp2; f_oo/f_ov/f_vv are built as make_moe_tensors does (cc.cpp:36-70: diagonal
+ * spin-orbital Fock blocks, F_ia = 0).  stages: 1 = MP2, 2 = +CCSD, 3 = +(T).  Optional outputs
+ * (may be NULL): e_hist[maxiter], T1[o,v], T2[o,o,v,v]. */
+int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
+                 const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, double *e_mp2,
+                 double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2);
+
 /* ---- building blocks exported for tests, benchmarks and other hosts ------------------ */
 /* BTAS-style contraction (the reference's only arithmetic primitive, e.g. cc.cpp:194):
  * C[ic] = beta*C[ic] + alpha * sum A[ia]*B[ib]; labels are single characters. */

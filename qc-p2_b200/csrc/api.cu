@@ -541,6 +541,62 @@ int qcp2_t_plan_destroy(qcp2_t_plan *plan) {
     return 0;
 }
 
+int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
+                 const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, double *e_mp2,
+                 double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(ao_ints && Ca && eps_a && e_mp2 && n >= 1, "post_hf: null argument");
+        QCP2_REQUIRE(stages >= 1 && stages <= 3, "post_hf: stages must be 1, 2 or 3");
+        if (uhf) QCP2_REQUIRE(Cb && eps_b, "post_hf: UHF needs Cb and eps_b");
+        if (stages >= 2) QCP2_REQUIRE(e_ccsd && maxiter >= 0, "post_hf: CCSD outputs missing");
+        if (stages >= 3) QCP2_REQUIRE(e_t, "post_hf: (T) output missing");
+        const long long n4 = ipow4(n), O = o, V = v, o2v2 = O * O * V * V;
+        const int n2 = 2 * n;
+        In ao(c, ao_ints, n4), ca(c, Ca, (long long) n * n), ea(c, eps_a, n);
+        In cb = uhf ? In(c, Cb, (long long) n * n) : In();
+        In eb = uhf ? In(c, eps_b, n) : In();
+        const double *pea = ea.p, *peb = uhf ? eb.p : ea.p;
+        DBuf t2_mp2(c, (size_t) std::max<long long>(o2v2, 1));
+        IntsDev I;
+        DBuf blocks[I_COUNT];
+        {
+            DBuf so(c, (size_t) (16 * n4));
+            mp2_dev(c, ao, ca, uhf ? cb.p : ca.p, pea, peb, n, o, v, uhf != 0, so, t2_mp2, e_mp2);// mp2.cpp:45-86
+            if (stages >= 2)
+                for (int k = 0; k < I_COUNT; ++k) {// get_integrals, cc.cpp:8-23
+                    blocks[k] = DBuf(c, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
+                    slice_block(c, so, n2, o, v, kIntNames[k], blocks[k]);
+                    I.p[k] = blocks[k].p;
+                }
+        }// the (2n)^4 tensor is released here
+        if (stages < 2) return;
+        DBuf foo(c, (size_t) (O * O)), fvv(c, (size_t) (V * V)), F(c, (size_t) ((long long) n2 * n2));
+        make_so_moes(c, pea, peb, n, F);// same diagonal as make_fock(eps_a, eps_b, 0, no+nv), cc.cpp:25-34
+        {
+            const long long oo[2] = {O, O}, so2[2] = {n2, 1};
+            permute_axpby(c, foo, F.p, 2, oo, so2, 1.0, 0.0);
+            const long long vv[2] = {V, V};
+            permute_axpby(c, fvv, F.p + O * n2 + O, 2, vv, so2, 1.0, 0.0);
+        }
+        Out t1(c, T1, O * V), t2(c, T2, o2v2);
+        DBuf t1own, t2own;
+        double *t1p = t1.p, *t2p = t2.p;
+        if (!t1p) t1own = DBuf(c, (size_t) std::max<long long>(O * V, 1)), t1p = t1own.p;
+        if (!t2p) t2own = DBuf(c, (size_t) std::max<long long>(o2v2, 1)), t2p = t2own.p;
+        ccsd_dev(c, I, foo, nullptr, fvv, t2_mp2, o, v, maxiter, conv, t1p, t2p, e_ccsd, iters, e_hist);// cc.cpp:409-451
+        t1.finish(), t2.finish();
+        if (stages >= 3) {// cc.cpp:454-560
+            DBuf eo(c, (size_t) std::max(o, 1)), ev(c, (size_t) std::max(v, 1));
+            extract_diag(c, foo, o, eo);
+            extract_diag(c, fvv, v, ev);
+            const int mode = t_select_mode(c, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], o, v);
+            std::unique_ptr<TPlan> plan(t_plan_create(c, t1p, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], eo, ev, o, v, mode));
+            t_plan_run(*plan, 0, 1, -1, nullptr, e_t);
+        }
+        c.sync();
+    });
+}
+
 // ---- building blocks ----------------------------------------------------------------
 int qcp2_contract(qcp2_ctx *ctx, double alpha, const double *A, const long long *extA, const char *ia,
                   const double *B, const long long *extB, const char *ib, double beta, double *C,

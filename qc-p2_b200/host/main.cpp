@@ -2,6 +2,7 @@
 // main.cpp:13-95; SCF on the host, MP2 / CCSD / (T) on the GPU through the C ABI.  Besides the
 // reference's setprecision(12) prints it writes machine-readable results with %.17g
 // (12 digits on a -76 Eh total are too coarse to assert 1e-10).
+#include <algorithm>
 #include <cstdio>
 #include <iomanip>
 #include <iostream>
@@ -15,8 +16,13 @@
 int main(int argc, char *argv[]) {
     using std::cout;
     using std::endl;
+    // `P2 --fused <input.json>`: same inputs and outputs, but MP2 -> CCSD -> (T) run as ONE device-
+    // resident call (qcp2_post_hf) instead of the reference's function-by-function sequence, which
+    // moves so_ints / sliced integrals through host memory between the stages.
+    bool fused = false;
+    if (argc >= 2 && std::string(argv[1]) == "--fused") fused = true, --argc, ++argv;
     if (argc < 2) {
-        std::cerr << "usage: P2 <input.json>" << endl;
+        std::cerr << "usage: P2 [--fused] <input.json>" << endl;
         return 2;
     }
     cout << std::setprecision(12);
@@ -45,6 +51,25 @@ int main(int argc, char *argv[]) {
             else if (is_uhf) hf = UHF(atoms, obs, nelectron, config, &ao);
             if (!hf.converged) throw std::runtime_error("SCF did not converge within maxiter (the reference leaves its results undefined here)");
             e_scf = hf.energy;
+            if (fused) {
+                const int stages = (t == "MP2" || t == "mp2") ? 1 : ((t == "CCSD" || t == "ccsd") ? 2 : 3);
+                int iters = 0;
+                std::vector<double> hist((size_t) std::max(config.maxiter, 1), 0.0);
+                gpu_check(qcp2_post_hf(gpu(), ao.data(), is_rhf ? hf.C.data() : hf.Ca.data(), is_rhf ? nullptr : hf.Cb.data(),
+                                       is_rhf ? hf.moes.data() : hf.moes_a.data(), is_rhf ? nullptr : hf.moes_b.data(), hf.nao, hf.no,
+                                       hf.nv, is_uhf ? 1 : 0, stages, config.maxiter, config.cc_conv, &e_mp2, &e_cc, &e_t, &iters,
+                                       hist.data(), nullptr, nullptr));
+                cout << "MP2 Energy: " << e_mp2 << " Eh" << endl;
+                if (stages >= 2) {
+                    for (int it = 0; it <= std::min(iters, config.maxiter - 1); ++it) printf(" %02d %20.12f\n", it, hist[(size_t) it]);
+                    cout << "CCSD energy: " << e_cc << " Eh" << endl;
+                }
+                if (stages >= 3) cout << "(T) energy: " << e_t << " Eh" << endl;
+                cout << "Total energy: " << e_scf + (stages >= 2 ? e_cc : e_mp2) + e_t << " Eh" << endl;
+                printf("RESULT {\"e_scf\": %.17g, \"e_mp2\": %.17g, \"e_ccsd\": %.17g, \"e_t\": %.17g}\n", e_scf, e_mp2, e_cc, e_t);
+                gpu_release();
+                return 0;
+            }
             auto mp2 = MP2(obs, hf, config, &ao);
             e_mp2 = mp2.energy;
             if (t == "MP2" || t == "mp2") {

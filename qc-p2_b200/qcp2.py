@@ -273,6 +273,25 @@ class Context:
             res["sliced_ints"] = dict(zip(INT_NAMES, sliced))
         return res
 
+    def post_hf(self, ao_ints, Ca, Cb, eps_a, eps_b, no, nv, uhf=False, stages=3, maxiter=200, cc_conv=1e-12,
+                want_amplitudes=False):
+        """Fused device-resident MP2 -> CCSD -> (T) (qcp2_post_hf): what main.cpp:76-88 runs after the SCF."""
+        ao, ca, ea = _arr(ao_ints), _arr(Ca), _arr(eps_a)
+        cb, eb = (_arr(Cb), _arr(eps_b)) if uhf else (None, None)
+        n = ao.shape[0]
+        e2, ecc, et, iters = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        hist = np.zeros(max(maxiter, 1))
+        T1 = np.empty((no, nv)) if want_amplitudes else None
+        T2 = np.empty((no, no, nv, nv)) if want_amplitudes else None
+        self.check(self.lib.qcp2_post_hf(self.h, _p(ao), _p(ca), _p(cb), _p(ea), _p(eb), n, no, nv, int(bool(uhf)), stages,
+                                         maxiter, C.c_double(cc_conv), C.byref(e2), C.byref(ecc), C.byref(et),
+                                         C.byref(iters), _p(hist), _p(T1), _p(T2)))
+        out = dict(e_mp2=e2.value, e_ccsd=ecc.value, e_t=et.value, iters=iters.value,
+                   e_hist=hist[:min(iters.value + 1, maxiter)])
+        if want_amplitudes:
+            out.update(T1=T1, T2=T2)
+        return out
+
     def t_count(self, o, mode):
         return int(self.lib.qcp2_ccsd_t_count(o, mode))
 

@@ -53,6 +53,19 @@ def test_config_energy_parity(ctx, name):
         assert abs(e_t - (-0.000099877272)) < 1e-11
 
 
+def test_config3_ch4_ccpvtz_fused_pipeline_vs_committed_cpu_oracle(ctx):
+    """BASELINE.json config 3 (o=10, v=162): the CPU side takes ~15 min, so its numbers are committed
+    (tests/golden/ch4_ccpvtz_oracle.json, generator beside it).  The host SCF is deterministic, so
+    the GPU box reproduces the same boundary inputs."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ch4_ccpvtz_oracle.json")))
+    case = molecule_case("methane.xyz", "cc-pvtz", conv=1e-10, maxiter=400)
+    assert (case["n"], case["no"], case["nv"]) == (86, 10, 162)
+    assert abs(case["e_scf"] - g["e_scf"]) < 1e-9
+    r = ctx.post_hf(case["ao"], case["C"], None, case["eps"], None, case["no"], case["nv"], stages=3, maxiter=200, cc_conv=1e-12)
+    assert abs(r["e_mp2"] - g["e_mp2"]) < E_TOL and abs(r["e_ccsd"] - g["e_ccsd"]) < E_TOL and abs(r["e_t"] - g["e_t"]) < E_TOL
+    assert r["iters"] == g["iters"] and np.max(np.abs(r["e_hist"] - np.array(g["e_hist"]))) < E_TOL
+
+
 def test_p2_driver_runs_reference_input_json(tmp_path):
     """The C++ host mirror end to end: bin/P2 on the reference's own input.json (water/STO-3G CCSD)
     and on a CCSD(T) variant of it; energies vs the Crawford known answers."""
@@ -71,3 +84,8 @@ def test_p2_driver_runs_reference_input_json(tmp_path):
     assert abs(r["e_ccsd"] - (-0.070680088376)) < 1e-10
     assert abs(r["e_t"] - (-0.000099877272)) < 1e-11
     assert "CC energy converged" in out.stdout
+    fused = subprocess.run([exe, "--fused", str(inp)], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert fused.returncode == 0, fused.stderr[-2000:]
+    rf = json.loads([l for l in fused.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    for key in ("e_mp2", "e_ccsd", "e_t"):
+        assert abs(rf[key] - r[key]) < 1e-13, key

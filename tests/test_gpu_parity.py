@@ -225,6 +225,21 @@ def test_full_pipeline_against_golden(ctx, name):
     assert abs(e_lit - g["e_t"]) < E_TOL
 
 
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_fused_post_hf_pipeline_against_golden(ctx, name):
+    g = GOLDEN[name]
+    spec = g["spec"]
+    uhf = spec["kind"] == "uhf"
+    case = uhf_case(spec["n"], spec["na"], spec["nb"], spec["seed"]) if uhf else rhf_case(spec["n"], spec["ndocc"], spec["seed"])
+    ea, eb = (case["eps_a"], case["eps_b"]) if uhf else (case["eps"], None)
+    r = ctx.post_hf(case["ao"], case["Ca"] if uhf else case["C"], case.get("Cb"), ea, eb, case["no"], case["nv"], uhf=uhf,
+                    stages=3, maxiter=100, cc_conv=1e-12)
+    assert abs(r["e_mp2"] - g["e_mp2"]) < E_TOL and abs(r["e_ccsd"] - g["e_ccsd"]) < E_TOL and abs(r["e_t"] - g["e_t"]) < E_TOL
+    assert r["iters"] == g["iters"] and np.max(np.abs(r["e_hist"] - np.array(g["e_hist"]))) < E_TOL
+    r1 = ctx.post_hf(case["ao"], case["Ca"] if uhf else case["C"], case.get("Cb"), ea, eb, case["no"], case["nv"], uhf=uhf, stages=1)
+    assert abs(r1["e_mp2"] - g["e_mp2"]) < E_TOL and r1["e_ccsd"] == 0.0
+
+
 def test_ccsd_from_presliced_blocks_and_maxiter_cap(ctx):
     case = rhf_case(6, 2, 51)
     r = oracle_pipeline(case, with_t=False, maxiter=4)          # stops at the cap, not converged

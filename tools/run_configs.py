@@ -54,7 +54,13 @@ def main():
         mode = ctx.t_select_mode(res["T2"], S["oovv"], S["vovv"], S["ovoo"])
         e_t = ctx.CCSD_T(res["T1"], res["T2"], S["oovv"], S["vovv"], S["ovoo"], eo, ev)
         t_t = time.time() - t0
+        t0 = time.time()
+        fused = ctx.post_hf(case["ao"], case["Ca"] if uhf else case["C"], case.get("Cb"), ea, eb if uhf else None, no, nv,
+                            uhf=uhf, stages=3, maxiter=200, cc_conv=1e-12)
+        t_fused = time.time() - t0
         rec = dict(n=case["n"], o=no, v=nv, e_scf=case["e_scf"], scf_seconds=t_scf,
+                   fused=dict(call_seconds=t_fused, e_mp2=fused["e_mp2"], e_ccsd=fused["e_ccsd"], e_t=fused["e_t"],
+                              iters=fused["iters"]),
                    gpu=dict(e_mp2=e_mp2, e_ccsd=res["ccsd_energy"], e_t=e_t, iters=res["iters"],
                             ccsd_loop_seconds=res["loop_seconds"], ccsd_s_per_iter=res["loop_seconds"] / max(res["iters"], 1),
                             mp2_call_seconds=t_mp2, ccsd_call_seconds=t_cc, t_call_seconds=t_t,
@@ -69,11 +75,11 @@ def main():
             cpu = dict(kind="oracle.cpp (literal)", e_mp2=ref["e_mp2"], e_ccsd=ref["e_ccsd"], e_t=e_t_ref, iters=ref["iters"],
                        hist_maxdiff=float(np.max(np.abs(np.array(ref["e_hist"]) - res["e_hist"]))))
         else:
-            In = {k: S[k] for k in qcp2_b200.INT_NAMES}  # same slices the GPU used (gathers are bit-exact, tested)
-            T2n, e2n = npo.mp2(In["oovv"], eo, ev)
-            t1, t2, hist = npo.ccsd(In, foo, fov, fvv, T2n, 200, 1e-12)
-            e_t_ref = npo.ccsd_t_blocked(t1, t2, In["oovv"], In["vovv"], In["ovoo"], eo, ev, True)
-            cpu = dict(kind="np_oracle (einsum)", e_mp2=e2n, e_ccsd=hist[-1], e_t=e_t_ref, iters=len(hist) - 1,
+            # ~15 min of CPU: use the committed CPU-oracle numbers (tests/golden/make_ch4_golden.py)
+            g = json.load(open(os.path.join(ROOT, "tests", "golden", "ch4_ccpvtz_oracle.json")))
+            hist = g["e_hist"]
+            cpu = dict(kind="np_oracle (einsum), committed fixture tests/golden/ch4_ccpvtz_oracle.json", e_mp2=g["e_mp2"],
+                       e_ccsd=g["e_ccsd"], e_t=g["e_t"], iters=g["iters"], fixture_seconds=g["seconds"],
                        hist_maxdiff=float(np.max(np.abs(np.array(hist) - res["e_hist"]))) if len(hist) == len(res["e_hist"]) else None)
         cpu["seconds"] = time.time() - t0
         rec["cpu"] = cpu

@@ -4,6 +4,8 @@
 // same index labels as the cited reference line, so the term list can be audited against
 // cc.cpp line by line; the elementwise pieces are the kernels of tensor_ops.cu.
 #include <cmath>
+#include <cstdlib>
+#include <vector>
 
 #include "contract.cuh"
 #include "dgemm.cuh"
@@ -171,7 +173,8 @@ void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
 // with tau = tau(Ts, Td) and tau_old / t_old the amplitudes the intermediates were built from
 // (Ts_old; cc.cpp:442-446 feeds make_T2 the NEW T1 but OLD intermediates).
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
-                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new, const double *Ts_old) {
+                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new, const double *Ts_old,
+                 const LadderPack *pack) {
     const long long O = o, V = v, o2v2 = O * O * V * V;
     const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
     const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
@@ -206,21 +209,51 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
         DBuf tau_old(ctx, (size_t) o2v2), y(ctx, (size_t) (O * O * O * O)), z(ctx, (size_t) (O * O * V * O));
         make_tau(ctx, Ts_old, Td, o, v, false, tau_old);
         const TView vtauo(tau_old.p, {O, O, V, V}), Y(y.p, {O, O, O, O}), Z(z.p, {O, O, V, O});
-        contract(ctx, 0.5, vtau, "ijef", vvvv, "abef", 1.0, R, "ijab");   // 1/2 tau <ab||ef>          (cc.cpp:240 in :348)
+        bool packed = false;
+        if (pack && pack->vvvvP && pack->npo > 0 && pack->npv > 0) {// tau must be antisymmetric for the e<f / i<j restriction
+            double d0, d1, m0, m1;
+            antisymmetry_defect(ctx, tau, O, O, V, V, 0, &d0, &m0);
+            antisymmetry_defect(ctx, tau, O, O, V, V, 1, &d1, &m1);
+            packed = d0 <= 1e-10 * m0 && d1 <= 1e-10 * m1;
+        }
+        if (packed) {
+            // sum over e<f only (x2 cancels the 1/2), rows i<j, columns a<b: 1/8 of the flops of the dense product
+            DBuf tauP(ctx, (size_t) pack->npo * pack->npv), lp(ctx, (size_t) pack->npo * pack->npv);
+            pack_pairs(ctx, tau, o, v, pack->pairs_o, pack->npo, tauP);
+            GemmArgs g;
+            g.M = pack->npo, g.N = pack->npv, g.K = pack->npv;
+            g.A = tauP, g.lda = pack->npv;         // [M][K]
+            g.B = pack->vvvvP, g.ldb = pack->npv;  // [N][K]
+            g.C = lp, g.ldc = pack->npv;
+            gemm(ctx, g, true, false);
+            unpack_add_pairs(ctx, lp, o, v, r);
+        } else {
+            contract(ctx, 0.5, vtau, "ijef", vvvv, "abef", 1.0, R, "ijab");// 1/2 tau <ab||ef>         (cc.cpp:240 in :348)
+        }
         contract(ctx, 1.0, vtau, "ijef", oovv, "mnef", 0.0, Y, "ijmn");   // 1/8 tau <mn||ef> tau_old  (cc.cpp:239 in :348)
         contract(ctx, 0.125, Y, "ijmn", vtauo, "mnab", 1.0, R, "ijab");
         contract(ctx, 1.0, vtau, "ijef", vovv, "amef", 0.0, Z, "ijam");   // -1/2 P(ab) tau <am||ef> t (cc.cpp:237-238 in :348)
         contract(ctx, -0.5, Z, "ijam", to, "mb", 1.0, R, "ijab");
         contract(ctx, 0.5, Z, "ijbm", to, "ma", 1.0, R, "ijab");
     }
-    contract(ctx, 1.0, td, "imae", Wmbej, "mbej", 1.0, R, "ijab");      // :354  ring terms
-    contract(ctx, -1.0, td, "jmae", Wmbej, "mbei", 1.0, R, "ijab");     // :355
-    contract(ctx, -1.0, td, "imbe", Wmbej, "maej", 1.0, R, "ijab");     // :356
-    contract(ctx, 1.0, td, "jmbe", Wmbej, "maei", 1.0, R, "ijab");      // :357
-    contract(ctx, 1.0, vtt, "iema", ovov, "mbje", 1.0, R, "ijab");      // :360
-    contract(ctx, -1.0, vtt, "jema", ovov, "mbie", 1.0, R, "ijab");     // :361
-    contract(ctx, -1.0, vtt, "iemb", ovov, "maje", 1.0, R, "ijab");     // :362
-    contract(ctx, 1.0, vtt, "jemb", ovov, "maie", 1.0, R, "ijab");      // :363
+    if (Wabef.p) {// literal: eight (ov)^3 products
+        contract(ctx, 1.0, td, "imae", Wmbej, "mbej", 1.0, R, "ijab");      // :354  ring terms
+        contract(ctx, -1.0, td, "jmae", Wmbej, "mbei", 1.0, R, "ijab");     // :355
+        contract(ctx, -1.0, td, "imbe", Wmbej, "maej", 1.0, R, "ijab");     // :356
+        contract(ctx, 1.0, td, "jmbe", Wmbej, "maei", 1.0, R, "ijab");      // :357
+        contract(ctx, 1.0, vtt, "iema", ovov, "mbje", 1.0, R, "ijab");      // :360
+        contract(ctx, -1.0, vtt, "jema", ovov, "mbie", 1.0, R, "ijab");     // :361
+        contract(ctx, -1.0, vtt, "iemb", ovov, "maje", 1.0, R, "ijab");     // :362
+        contract(ctx, 1.0, vtt, "jemb", ovov, "maie", 1.0, R, "ijab");      // :363
+    } else {
+        // fused solver: cc.cpp:354-357 are ONE product Rt[i,a,b,j] = sum_me t_imae W_mbej evaluated at four
+        // index relabelings, likewise :360-363 with (t_ie t_ma) <mb||je>; two GEMMs + one P(ij)P(ab) combine
+        DBuf rt(ctx, (size_t) o2v2);
+        const TView Rt(rt.p, {O, V, V, O});
+        contract(ctx, 1.0, td, "imae", Wmbej, "mbej", 0.0, Rt, "iabj");
+        contract(ctx, 1.0, vtt, "iema", ovov, "mbje", 1.0, Rt, "iabj");
+        ring_combine(ctx, rt, o, v, r);
+    }
     contract(ctx, 1.0, ts, "ie", vvvo, "abej", 1.0, R, "ijab");         // :366
     contract(ctx, -1.0, ts, "je", vvvo, "abei", 1.0, R, "ijab");        // :367
     contract(ctx, -1.0, ts, "ma", ovoo, "mbij", 1.0, R, "ijab");        // :370
@@ -243,6 +276,30 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         xbuf[k] = DBuf(ctx, (size_t) inter_block_size(k, o, v)), X.p[k] = xbuf[k].p;
     }
     DBuf t1n(ctx, (size_t) (O * V)), t2n(ctx, (size_t) o2v2), e_dev(ctx, 1);
+    // packed particle-particle ladder operands, only when <vv||vv> has both antisymmetries (RHF-type inputs;
+    // the as-written UHF integrals lose the ket antisymmetry, SURVEY.md Q5, and take the dense product)
+    LadderPack pack;
+    DBuf vvvvP;
+    int *pairs_dev = nullptr;
+    if (o >= 2 && v >= 2 && !getenv("QCP2_CCSD_DENSE_LADDER")) {
+        double d0, d1, m0, m1;
+        antisymmetry_defect(ctx, I.p[I_VVVV], V, V, V, V, 0, &d0, &m0);
+        antisymmetry_defect(ctx, I.p[I_VVVV], V, V, V, V, 1, &d1, &m1);
+        if (d0 <= 1e-10 * m0 && d1 <= 1e-10 * m1) {
+            std::vector<int> po, pv;
+            for (int i = 0; i < o; ++i)
+                for (int j = i + 1; j < o; ++j) po.push_back(i), po.push_back(j);
+            for (int a = 0; a < v; ++a)
+                for (int b = a + 1; b < v; ++b) pv.push_back(a), pv.push_back(b);
+            QCP2_CUDA(cudaMalloc(&pairs_dev, (po.size() + pv.size()) * sizeof(int)));
+            QCP2_CUDA(cudaMemcpy(pairs_dev, po.data(), po.size() * sizeof(int), cudaMemcpyHostToDevice));
+            QCP2_CUDA(cudaMemcpy(pairs_dev + po.size(), pv.data(), pv.size() * sizeof(int), cudaMemcpyHostToDevice));
+            pack.npo = (int) (po.size() / 2), pack.npv = (int) (pv.size() / 2);
+            vvvvP = DBuf(ctx, (size_t) pack.npv * pack.npv);
+            pack_pairs(ctx, I.p[I_VVVV], v, v, pairs_dev + po.size(), pack.npv, vvvvP);
+            pack.vvvvP = vvvvP.p, pack.pairs_o = pairs_dev;
+        }
+    }
     fill_zero(ctx, T1, O * V);                                                             // :417-419
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
     cudaEvent_t ev0, ev1;
@@ -261,7 +318,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         if (std::fabs(de) < conv) break;                                                   // :438 (fabs)
         update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
         make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);                          // :445
-        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1);                              // :446: new T1, old T2, old X
+        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1, &pack);                              // :446: new T1, old T2, old X
         QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     }
@@ -272,6 +329,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     ctx.ccsd_loop_seconds = ms * 1e-3;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    if (pairs_dev) cudaFree(pairs_dev);
     *e_host = e;
     if (iters_host) *iters_host = it;
 }

@@ -9,6 +9,13 @@ enum IntBlock { I_OOOO, I_OVOO, I_OOVO, I_OOOV, I_OVOV, I_OVVO, I_OOVV, I_VOVV, 
 extern const char *const kIntNames[I_COUNT];
 enum InterBlock { X_FAE, X_FMI, X_FME, X_WMNIJ, X_WMBEJ, X_WABEF, X_COUNT };
 
+// b<c / i<j packed operands of the particle-particle ladder (valid for antisymmetric integrals only)
+struct LadderPack {
+    const double *vvvvP = nullptr;// [v(v-1)/2][v(v-1)/2]
+    const int *pairs_o = nullptr; // device, 2 ints per i<j pair
+    int npo = 0, npv = 0;
+};
+
 struct IntsDev {
     const double *p[I_COUNT];
 };
@@ -29,7 +36,7 @@ void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
                  const double *fov, const double *fvv, const double *D_ia, int o, int v, double *T1_new);
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
                  const double *fvv, const double *D_ijab, int o, int v, double *T2_new,
-                 const double *Ts_old = nullptr);
+                 const double *Ts_old = nullptr, const struct LadderPack *pack = nullptr);
 void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,
               const double *T2_guess, int o, int v, int maxiter, double conv, double *T1, double *T2, double *e_host,
               int *iters_host, double *e_hist_host);

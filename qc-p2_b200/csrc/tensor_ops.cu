@@ -476,6 +476,76 @@ void divide_elementwise(Ctx &ctx, const double *r, const double *D, long long n,
     ctx.launched("divide");
 }
 
+__global__ void ring_combine_kernel(const double *__restrict__ Rt, int o, int v, double *__restrict__ r) {
+    const long long n = (long long) o * o * v * v;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        const int b = (int) (q % v);
+        q /= v;
+        const int a = (int) (q % v);
+        q /= v;
+        const int j = (int) (q % o);
+        const int i = (int) (q / o);
+        auto at = [&](int x, int c, int d, int y) { return Rt[(((long long) x * v + c) * v + d) * o + y]; };
+        r[lin] += at(i, a, b, j) - at(j, a, b, i) - at(i, b, a, j) + at(j, b, a, i);
+    }
+}
+void ring_combine(Ctx &ctx, const double *Rt, int o, int v, double *r) {
+    const long long n = (long long) o * o * v * v;
+    if (n == 0) return;
+    ring_combine_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(Rt, o, v, r);
+    ctx.launched("ring_combine");
+}
+
+__global__ void pack_pairs_kernel(const double *__restrict__ src, int d01, int d23, const int *__restrict__ pairs01,
+                                  double *__restrict__ dst) {
+    const int a = pairs01[2 * blockIdx.x], b = pairs01[2 * blockIdx.x + 1];
+    const size_t n23 = (size_t) d23 * (d23 - 1) / 2;
+    const double *s = src + ((size_t) a * d01 + b) * d23 * d23;
+    double *d = dst + (size_t) blockIdx.x * n23;
+    for (int e = 0; e + 1 < d23; ++e) {
+        const size_t q0 = (size_t) e * d23 - (size_t) e * (e + 1) / 2 - (e + 1);// q(e,f) = q0 + f
+        for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) d[q0 + f] = s[(size_t) e * d23 + f];
+    }
+}
+void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst) {
+    if (n01 <= 0 || d23 < 2) return;
+    pack_pairs_kernel<<<(unsigned) n01, kBlock, 0, ctx.stream>>>(src, d01, d23, pairs01, dst);
+    ctx.launched("pack_pairs");
+}
+
+__global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, int o, int v, double *__restrict__ r) {
+    const long long n = (long long) o * o * v * v, npv = (long long) v * (v - 1) / 2;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        int b = (int) (q % v);
+        q /= v;
+        int a = (int) (q % v);
+        q /= v;
+        int j = (int) (q % o);
+        int i = (int) (q / o);
+        if (i == j || a == b) continue;
+        double sign = 1.0;
+        if (i > j) {
+            const int t = i;
+            i = j, j = t, sign = -sign;
+        }
+        if (a > b) {
+            const int t = a;
+            a = b, b = t, sign = -sign;
+        }
+        const long long pij = (long long) i * o - (long long) i * (i + 1) / 2 + (j - i - 1);
+        const long long pab = (long long) a * v - (long long) a * (a + 1) / 2 + (b - a - 1);
+        r[lin] += sign * LP[pij * npv + pab];
+    }
+}
+void unpack_add_pairs(Ctx &ctx, const double *LP, int o, int v, double *r) {
+    const long long n = (long long) o * o * v * v;
+    if (n == 0 || o < 2 || v < 2) return;
+    unpack_add_pairs_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(LP, o, v, r);
+    ctx.launched("unpack_add_pairs");
+}
+
 __global__ void diag_kernel(const double *__restrict__ F, int n, double *__restrict__ d) {
     GRID_STRIDE(i, (long long) n) d[i] = F[i * n + i];
 }

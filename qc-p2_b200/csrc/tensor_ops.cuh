@@ -33,6 +33,13 @@ void divide_elementwise(Ctx &ctx, const double *r, const double *D, long long n,
 void ccsd_energy(Ctx &ctx, const double *Ts, const double *Td, const double *oovv, const double *fov, int o, int v,
                  double *e_dev);
 void extract_diag(Ctx &ctx, const double *F, int n, double *d);
+// r[i,j,a,b] += Rt[i,a,b,j] - Rt[j,a,b,i] - Rt[i,b,a,j] + Rt[j,b,a,i]   (P(ij)P(ab) of one ring product)
+void ring_combine(Ctx &ctx, const double *Rt, int o, int v, double *r);
+
+// dst[row][q(e<f)] = src[a_row][b_row][e][f] for the rows (a<b) listed in pairs01 (2 ints per row); src is [d01,d01,d23,d23]
+void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst);
+// r[i,j,a,b] += sgn(ij) sgn(ab) LP[p(i,j)][p(a,b)]  (zero on the diagonals); LP is [o(o-1)/2][v(v-1)/2]
+void unpack_add_pairs(Ctx &ctx, const double *LP, int o, int v, double *r);
 
 // max |x + P x| over an index-pair transposition, relative to max|x| -> host values
 void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,

@@ -271,10 +271,11 @@ def ccsd_t_blocked(T1, T2, oovv, vovv, ovoo, eo, ev, symmetric):
     return e / 36.0
 
 
-def ccsd_t_triple_packed_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k, bu=None, cu=None):
+def ccsd_t_triple_packed_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k, bu=None, cu=None, fast=False):
     """CPU baseline kernel for config 5: one i<j<k triple with b<c column packing
     (M=v, N=v(v-1)/2, K=3(v+o) GEMM via BLAS) and the a<b<c energy sum; returns the triple's
-    contribution to E(T) (already including the 6*6/36 weight)."""
+    contribution to E(T) (already including the 6*6/36 weight).  fast=True hands the energy sum to
+    the OpenMP loop in oracle.cpp (all host threads) instead of whole-cube numpy passes."""
     o, v = T1.shape
     if bu is None:
         bu, cu = np.triu_indices(v, 1)
@@ -283,6 +284,9 @@ def ccsd_t_triple_packed_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k, bu=None, 
     B = np.concatenate([vovv[:, i][:, bu, cu], vovv[:, j][:, bu, cu], vovv[:, k][:, bu, cu],
                         T2[i][:, bu, cu], T2[j][:, bu, cu], T2[k][:, bu, cu]], axis=0)
     Xp = A @ B  # [v, NP]
+    if fast:
+        from oracle import oracle as _orc
+        return _orc.t_energy_packed(Xp, T1, oovv, eo, ev, i, j, k)
     X = np.zeros((v, v, v))
     X[:, bu, cu] = Xp
     X[:, cu, bu] = -Xp
@@ -294,6 +298,41 @@ def ccsd_t_triple_packed_np(T1, T2, oovv, vovv, ovoo, eo, ev, i, j, k, bu=None, 
     # W(W+V)/D is totally symmetric in (a,b,c) and vanishes on the diagonals, so the a<b<c sum is
     # one sixth of the full-cube sum (avoids building index masks)
     return float(np.sum(W * (W + V) / D)) / 6.0
+
+
+class PackedTriples:
+    """CPU baseline for config 5 organised like a real run: the b<c-packed slabs vovvP[i] (v x NP) and
+    T2P[i] (o x NP) are built once per occupied index and reused by every triple that touches it (in the
+    full job each slab serves ~740 triples), X = sum of six BLAS GEMMs, OpenMP energy sweep."""
+
+    def __init__(self, T1, T2, oovv, vovv, ovoo, eo, ev):
+        self.T1, self.T2, self.oovv, self.vovv, self.ovoo = T1, T2, np.ascontiguousarray(oovv), vovv, ovoo
+        self.eo, self.ev = np.ascontiguousarray(eo), np.ascontiguousarray(ev)
+        self.o, self.v = T1.shape
+        self.bu, self.cu = np.triu_indices(self.v, 1)
+        self._vovvP, self._T2P = {}, {}
+
+    def slabs(self, i):
+        if i not in self._vovvP:
+            self._vovvP[i] = np.ascontiguousarray(self.vovv[:, i][:, self.bu, self.cu])
+            self._T2P[i] = np.ascontiguousarray(self.T2[i][:, self.bu, self.cu])
+        return self._vovvP[i], self._T2P[i]
+
+    def prepare(self, occ):
+        for i in occ:
+            self.slabs(int(i))
+
+    def triple(self, i, j, k):
+        from oracle import oracle as _orc
+        T2, ovoo = self.T2, self.ovoo
+        (Vi, Ti), (Vj, Tj), (Vk, Tk) = self.slabs(i), self.slabs(j), self.slabs(k)
+        Xp = T2[j, k] @ Vi
+        Xp -= T2[i, k] @ Vj
+        Xp -= T2[j, i] @ Vk
+        Xp -= ovoo[:, :, j, k].T @ Ti
+        Xp += ovoo[:, :, i, k].T @ Tj
+        Xp += ovoo[:, :, j, i].T @ Tk
+        return _orc.t_energy_packed(Xp, self.T1, self.oovv, self.eo, self.ev, i, j, k)
 
 
 def t_flops(o, v, ntriples=None):

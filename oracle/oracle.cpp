@@ -578,6 +578,37 @@ static double ccsd_t_blocked(const Tensor &T1, const Tensor &T2, const Tensor &o
     return total / 36;
 }
 
+// Energy sweep of one sorted triple from the b<c-packed X = A.B (CPU baseline only): the same
+// W / V / D arithmetic as ccsd_t_blocked restricted to a<b<c (needs antisymmetric inputs), all
+// host threads, no copies of the big tensors.  Returns sum_{a<b<c} W (W+V) / D, i.e. the triple's
+// full contribution to E(T).
+static double t_energy_packed(const double *Xp, const double *T1, const double *oovv, const double *eo, const double *ev,
+                              long o, long v, long i, long j, long k) {
+    const long np = v * (v - 1) / 2;
+    auto pidx = [v](long b, long c) { return b * v - b * (b + 1) / 2 + (c - b - 1); };
+    const double dijk = eo[i] + eo[j] + eo[k];
+    const double *Ojk = oovv + (j * o + k) * v * v, *Oik = oovv + (i * o + k) * v * v, *Oji = oovv + (j * o + i) * v * v;
+    const double *ti = T1 + i * v, *tj = T1 + j * v, *tk = T1 + k * v;
+    double total = 0.0;
+#pragma omp parallel for reduction(+ : total) schedule(dynamic, 4)
+    for (long a = 0; a < v - 2; ++a) {
+        double acc = 0.0;
+        for (long b = a + 1; b < v - 1; ++b) {
+            const long pab = pidx(a, b);
+            for (long c = b + 1; c < v; ++c) {
+                const long pbc = pidx(b, c), pac = pidx(a, c);
+                const double W = Xp[a * np + pbc] - Xp[b * np + pac] + Xp[c * np + pab];
+                const double Ya = ti[a] * Ojk[b * v + c] - tj[a] * Oik[b * v + c] - tk[a] * Oji[b * v + c];
+                const double Yb = ti[b] * Ojk[a * v + c] - tj[b] * Oik[a * v + c] - tk[b] * Oji[a * v + c];
+                const double Yc = ti[c] * Ojk[a * v + b] - tj[c] * Oik[a * v + b] - tk[c] * Oji[a * v + b];
+                acc += W * (W + (Ya - Yb + Yc)) / (dijk - ev[a] - ev[b] - ev[c]);
+            }
+        }
+        total += acc;
+    }
+    return total;
+}
+
 }// namespace orc
 
 // ---------------------------------------------------------------------------------
@@ -770,6 +801,13 @@ int orc_ccsd_t(const double *T1, const double *T2, const double *oovv, const dou
     I.ovoo = Tensor(Ext{no, nv, no, no}, ovoo);
     *E = orc::ccsd_t_literal(Tensor(Ext{no, nv}, T1), Tensor(Ext{no, no, nv, nv}, T2), I,
                              wrap_moes(foo, nullptr, fvv, no, nv));
+    ORC_CATCH
+}
+
+int orc_t_energy_packed(const double *Xp, const double *T1, const double *oovv, const double *eps_o, const double *eps_v,
+                        int no, int nv, int i, int j, int k, double *E) {
+    ORC_TRY
+    *E = orc::t_energy_packed(Xp, T1, oovv, eps_o, eps_v, no, nv, i, j, k);
     ORC_CATCH
 }
 

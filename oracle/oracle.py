@@ -209,3 +209,14 @@ def ccsd_t_blocked(T1, T2, oovv, vovv, ovoo, eo, ev, triples, weight=1.0):
                                   T1.shape[1], tr.ctypes.data_as(C.POINTER(C.c_int)), C.c_long(tr.shape[0]),
                                   C.c_double(weight), C.byref(E)))
     return E.value
+
+
+def t_energy_packed(Xp, T1, oovv, eo, ev, i, j, k):
+    """sum_{a<b<c} W (W+V)/D of one sorted triple from the b<c-packed X (OpenMP; CPU baseline)."""
+    Xp, T1, eo, ev = map(_c, (Xp, T1, eo, ev))
+    if not (oovv.flags["C_CONTIGUOUS"] and oovv.dtype == np.float64):
+        oovv = _c(oovv)
+    E = C.c_double()
+    _chk(lib().orc_t_energy_packed(_p(Xp), _p(T1), _p(oovv), _p(eo), _p(ev), T1.shape[0], T1.shape[1], int(i), int(j), int(k),
+                                   C.byref(E)))
+    return E.value

@@ -115,6 +115,10 @@ def test_synthetic_t_literal_vs_symmetric_vs_packed():
     sym = npo.ccsd_t_blocked(*args, True)
     ein = npo.ccsd_t_einsum(*args)
     packed = sum(npo.ccsd_t_triple_packed_np(*args, int(i), int(j), int(k)) for i, j, k in npo.sorted_triples(4))
+    packed_fast = sum(npo.ccsd_t_triple_packed_np(*args, int(i), int(j), int(k), fast=True) for i, j, k in npo.sorted_triples(4))
+    assert abs(packed_fast - packed) < 1e-14 * max(1.0, abs(packed))
+    pk = npo.PackedTriples(*args)
+    assert abs(sum(pk.triple(int(i), int(j), int(k)) for i, j, k in npo.sorted_triples(4)) - packed) < 1e-14 * max(1.0, abs(packed))
     foo, fvv = np.diag(s["eps_o"]), np.diag(s["eps_v"])
     cpp = orc.ccsd_t(s["T1"], s["T2"], s["oovv"], s["vovv"], s["ovoo"], foo, fvv)
     for x in (sym, ein, packed, cpp):

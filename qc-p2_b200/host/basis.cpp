@@ -7,7 +7,7 @@
 // normalised primitives has norm 1 within 1e-3, tests/test_host_cpu.py) and (ii) the known
 // answers quoted in tests/test_known_answers.py.  Energies depend only on the SPAN of the basis,
 // so normalisation and function ordering conventions do not matter; a mistyped digit would
-// shift total energies but cannot affect GPU-vs-oracle parity, which is asserted at the hot-path
+// shift total energies but cannot affect GPU-vs-CPU parity, which is asserted at the hot-path
 // boundary on identical inputs.
 #include "basis.h"
 

@@ -6,8 +6,9 @@ eqs. 1-13; Crawford ProgrammingProjects #6 for (T)) rather than from oracle.cpp,
 oracles check each other.  Reference call sites: src/integrals.cpp:95-207,
 src/mp2.cpp:11-42, src/cc.cpp:125-560.
 
-PARITY UNPINNED against the reference binary (it cannot be built here and ships no golden
-vectors); pinned only to the external Crawford water/STO-3G numbers.
+Pinned through oracle.cpp, which tests/test_ref_pins_oracle.py holds against the reference's own
+sources compiled under oracle/_ref (see oracle/ref.py), and to the external Crawford
+water/STO-3G numbers.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 may import this module.

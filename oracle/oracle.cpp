@@ -6,14 +6,18 @@
 // only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 // legs use it.
 //
-// PARITY UNPINNED w.r.t. the reference binary: the reference cannot be built here
-// (Libint2/BTAS/Eigen absent, no network) and ships no tests or golden vectors
-// (SURVEY.md section 8c).  The arithmetic of the path lives in BTAS
-// (github.com/ValeevGroup/btas, unpinned master, CMakeLists.txt:9-13); its
-// `contract(alpha,A,ia,B,ib,beta,C,ic)` is restated here from its published meaning
-// C[ic] = beta*C[ic] + alpha * sum_{shared} A[ia]*B[ib].  The only external anchor is
-// the Crawford ProgrammingProjects water/STO-3G known answers (cc.cpp:453), checked in
-// tests/test_known_answers.py through the host SCF substrate.
+// PARITY PIN: the reference's own sources (src/{integrals,mp2,cc,hf,general}.cpp, unmodified,
+// compiled where they lie by oracle/ref_shim/Makefile against API stand-ins for the absent
+// third-party headers, output oracle/_ref/) are run beside this restatement by
+// tests/test_ref_pins_oracle.py: every function of SURVEY.md section 8a, RHF and as-written
+// UHF, agrees to rounding (bit-identical energies on the seeded cases), and the reference
+// program's results on BASELINE.json configs 1, 2, 4 are committed as
+// tests/golden/reference_energies.json.  What remains restated rather than run is the
+// third-party arithmetic itself: BTAS (github.com/ValeevGroup/btas, unpinned master,
+// CMakeLists.txt:9-13) is not in this image, so `contract(alpha,A,ia,B,ib,beta,C,ic)` means,
+// here and in the shim, its published C[ic] = beta*C[ic] + alpha * sum_{shared} A[ia]*B[ib].
+// External anchor: the Crawford ProgrammingProjects water/STO-3G known answers (cc.cpp:453),
+// tests/test_known_answers.py.
 //
 // Written as an index-string (einsum-like) engine so each reference contraction is one
 // line whose labels can be compared with the cited reference line.

@@ -1,5 +1,6 @@
 """oracle/oracle.py -- TEST INFRASTRUCTURE ONLY: ctypes front end of oracle/liboracle.so
-(the literal C++ restatement in oracle.cpp).  PARITY UNPINNED, see oracle.cpp header.
+(the literal C++ restatement in oracle.cpp).  Pinned against the compiled reference sources
+(oracle/ref.py, tests/test_ref_pins_oracle.py); see the oracle.cpp header.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 may import this module; the product path (qc-p2_b200/) never does.

@@ -308,6 +308,10 @@ def main():
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_pointer_mode(qcp2_b200.DEVICE)
+    if world > 1:
+        # the library's own NCCL communicator (qcp2_comm_*); torch.distributed only carries the
+        # 128-byte bootstrap id, the barriers and the max-over-ranks of the timings
+        ctx.comm_init_from_torch(dist)
 
     # ---- inputs: rank 0 generates, NCCL broadcast replicates (outside the timed region for `value`)
     d = qcp2_b200.synth_t_inputs_device(ctx, o, v)
@@ -316,7 +320,8 @@ def main():
         if rank != 0:
             for k in names:
                 d[k].zero_()
-        qcp2_b200.shard.broadcast_inputs([d[k] for k in names], dist, src=0)
+        for k in names:
+            ctx.comm_broadcast(d[k], root=0)
     plan = qcp2_b200.DeviceTriples(ctx, *(d[k] for k in names), qcp2_b200.T_SYMMETRIC)
     nt = ctx.t_count(o, qcp2_b200.T_SYMMETRIC)
     e_trip = torch.zeros(nt, dtype=torch.float64, device="cuda")
@@ -327,7 +332,9 @@ def main():
         e_trip.zero_()
         plan.run(first, world, B, e_trip)
         tm = plan.timings()
-        total = qcp2_b200.shard.reduce_triple_energies(e_trip, dist if world > 1 else None)
+        if world > 1:
+            ctx.comm_allreduce_sum(e_trip)  # one slot per triple, written by exactly one rank: exact
+        total = qcp2_b200.shard.reduce_triple_energies(e_trip, None)  # fixed-order host sum
         done = len(range(first, nt, world)[:B])
         return total, tm, done
 
@@ -407,19 +414,12 @@ def main():
             e_job = ctx.CCSD_T(*(host[k].numpy() for k in names), qcp2_b200.T_AUTO)
             ctx.set_pointer_mode(qcp2_b200.DEVICE)
         else:
-            dd = {}
-            for k in names:
-                shape = {"T1": (o, v), "T2": (o, o, v, v), "oovv": (o, o, v, v), "vovv": (v, o, v, v), "ovoo": (o, v, o, o),
-                         "eps_o": (o,), "eps_v": (v,)}[k]
-                dd[k] = torch.empty(shape, dtype=torch.float64, device="cuda")
-                if rank == 0:
-                    dd[k].copy_(host[k], non_blocking=True)
-            qcp2_b200.shard.broadcast_inputs([dd[k] for k in names], dist, src=0)
-            p2 = qcp2_b200.DeviceTriples(ctx, *(dd[k] for k in names), qcp2_b200.T_SYMMETRIC)
-            e_trip.zero_()
-            p2.run(rank, world, -1, e_trip)
-            e_job = qcp2_b200.shard.reduce_triple_energies(e_trip, dist)
-            p2.close()
+            # qcp2_ccsd_t_mgpu: rank 0 stages its pinned host tensors, ncclBroadcast replicates them,
+            # every rank evaluates its round-robin share, one ncclAllReduce of the per-triple vector
+            ctx.set_pointer_mode(qcp2_b200.HOST)
+            src = [host[k].numpy() if rank == 0 else None for k in names]
+            e_job = ctx.CCSD_T_mgpu(*src, o, v, qcp2_b200.T_AUTO, root=0)
+            ctx.set_pointer_mode(qcp2_b200.DEVICE)
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -427,7 +427,7 @@ def main():
         e2e = {"value": nt * fpt / float(dt[0]) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d if rank == 0 else 0,
                "d2h_bytes_per_step": 8 * (nt + 1), "steps": 1, "seconds": float(dt[0]), "e_t": e_job,
                "what": "whole (T) job (all %d triples) via qcp2_ccsd_t with pinned host buffers" % nt if world == 1 else
-                       "whole (T) job: rank-0 pinned host buffers -> H2D -> NCCL broadcast -> sharded triples -> all-reduce"}
+                       "whole (T) job via qcp2_ccsd_t_mgpu: rank-0 pinned host buffers -> H2D -> ncclBroadcast -> round-robin triples -> ncclAllReduce"}
 
     ccsd = None
     if rank == 0 and not args.no_ccsd:
@@ -453,9 +453,9 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "ccsd": ccsd, "energy_checksum": energy_acc}
         print(json.dumps(line), flush=True)
+    ctx.close()  # also destroys the library's communicator
     if world > 1:
         dist.destroy_process_group()
-    ctx.close()
 
 
 if __name__ == "__main__":

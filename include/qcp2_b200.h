@@ -136,6 +136,32 @@ long long qcp2_ccsd_t_count(int o, int mode);
 int qcp2_ccsd_t_select_mode(qcp2_ctx *ctx, const double *T2, const double *oovv, const double *vovv,
                             const double *ovoo, int o, int v, int *mode);
 
+/* ---- multi-GPU: one process (rank) per GPU, NCCL over NVLink 5 / NVSwitch -------------
+ * The reference is single-process; these entry points are the sharded form of CCSD_T
+ * (cc.cpp:454-560) of SURVEY.md section 8e.  NCCL is bound at run time (libnccl.so.2).
+ * Bootstrap: rank 0 calls qcp2_comm_get_unique_id and hands the 128 bytes to the other ranks
+ * by any host channel (pipe, file, MPI, torch.distributed ...); every rank then calls
+ * qcp2_comm_init on its own context (collective). */
+#define QCP2_COMM_ID_BYTES 128
+int qcp2_comm_get_unique_id(void *id, int id_bytes);
+int qcp2_comm_init(qcp2_ctx *ctx, const void *id, int nranks, int rank);
+int qcp2_comm_destroy(qcp2_ctx *ctx);
+int qcp2_comm_rank(const qcp2_ctx *ctx, int *rank, int *nranks); /* (0, 1) without a communicator */
+/* stream-ordered collectives on DEVICE buffers of doubles (no-ops / local copy on a single rank) */
+int qcp2_comm_broadcast(qcp2_ctx *ctx, double *dev_buf, long long n, int root);
+int qcp2_comm_allreduce_sum(qcp2_ctx *ctx, double *dev_buf, long long n);
+int qcp2_comm_allgather(qcp2_ctx *ctx, const double *dev_send, double *dev_recv, long long n_per_rank);
+/* CCSD_T across the communicator (collective; every rank calls it with the same o, v, mode,
+ * root).  Rank `root` supplies the tensors (host or device pointers per its pointer mode); the
+ * other ranks may pass NULL.  The inputs are replicated by ncclBroadcast, rank r evaluates the
+ * triples {r, r+W, r+2W, ...} of the mode's enumeration, one ncclAllReduce combines the
+ * per-triple energy vector and every rank returns the same, fixed-order sum in *energy:
+ * bit-identical to qcp2_ccsd_t for any number of ranks.  e_triples (host, qcp2_ccsd_t_count()
+ * doubles) may be NULL. */
+int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode, int root,
+                     double *e_triples, double *energy);
+
 /* Resident (T) plan: packs/repacks the inputs once (device pointers required) so repeated
  * range evaluations (bench steps, multi-rank shards) reuse them. */
 typedef struct qcp2_t_plan qcp2_t_plan;

@@ -1,12 +1,15 @@
 // api.cu -- the C ABI of include/qcp2_b200.h: argument checking, host<->device marshalling
 // for QCP2_HOST pointer mode, exception -> status translation.  No arithmetic happens here
 // and there is no CPU path: every entry point ends in kernels on the context's device.
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/qcp2_b200.h"
+#include "comm.cuh"
 #include "contract.cuh"
 #include "dgemm.cuh"
 #include "post_hf.cuh"
@@ -17,6 +20,7 @@ using namespace qcp2;
 
 struct qcp2_ctx {
     Ctx c;
+    Comm *comm = nullptr;// NCCL communicator (qcp2_comm_init); null = single GPU
 };
 struct qcp2_t_plan {
     qcp2_ctx *owner = nullptr;
@@ -75,6 +79,22 @@ int guarded(qcp2_ctx *ctx, F &&f) {
 
 long long ipow4(long long n) { return n * n * n * n; }
 
+// QCP2_TRACE=1: wall-clock phase marks (each mark synchronises the stream) on stderr
+struct Trace {
+    Ctx &c;
+    const char *what;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace(Ctx &ctx, const char *w) : c(ctx), what(w), on(getenv("QCP2_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *phase) {
+        if (!on) return;
+        c.sync();
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[qcp2 trace] %s: %-44s %9.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 }// namespace
 
 extern "C" {
@@ -116,6 +136,13 @@ int qcp2_destroy(qcp2_ctx *ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
+    if (ctx->comm) {
+        try {
+            comm_destroy(ctx->comm);
+        } catch (...) {
+        }
+        ctx->comm = nullptr;
+    }
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.own_stream);
     delete ctx;
     return 0;
@@ -462,28 +489,75 @@ int qcp2_ccsd_t_select_mode(qcp2_ctx *ctx, const double *T2, const double *oovv,
     });
 }
 
+// Shared body of qcp2_ccsd_t_range / qcp2_ccsd_t_mgpu once the small tensors are on the device.
+// vovv_dev: device <vo||vv> (classic path) or null; vovv_host + streamed: the root's host tensor is
+// streamed slab by slab (SYMMETRIC only).  Returns the per-triple vector on the device in `et`.
+namespace {
+struct TEval {
+    std::unique_ptr<TPlan> plan;
+    DBuf et;
+    long long nt = 0;
+    double partial = 0.0;
+};
+void t_evaluate(Ctx &c, TEval &ev_, const double *t1, const double *t2, const double *g, const double *vovv_dev, const double *x,
+                const double *eo, const double *ev, int o, int v, int m, const TStream *ts, long long first, long long stride,
+                long long max_count, bool want_vector, Trace &tr) {
+    ev_.plan.reset(t_plan_create(c, t1, t2, g, vovv_dev, x, eo, ev, o, v, m, ts));
+    tr.mark(ts ? "plan (pack b<c, workspaces, slab stream enqueued)" : "plan (pack b<c, workspaces)");
+    ev_.nt = ev_.plan->ntriples;
+    if (want_vector) {
+        ev_.et = DBuf(c, (size_t) std::max<long long>(ev_.nt, 1));
+        fill_zero(c, ev_.et, ev_.nt);
+    }
+    t_plan_run(*ev_.plan, first, stride, max_count, want_vector ? ev_.et.p : nullptr, &ev_.partial);
+    tr.mark("run triples");
+}
+bool stream_allowed(const Ctx &c, int mode, int o, int v) {
+    return c.pointer_mode == QCP2_HOST && mode != QCP2_T_LITERAL && v >= 2 && t_count(o, QCP2_T_SYMMETRIC) > 0 &&
+           !getenv("QCP2_T_NO_STREAM");
+}
+}// namespace
+
 int qcp2_ccsd_t_range(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
                       const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
                       long long first, long long stride, long long max_count, double *e_triples, double *energy) {
     return guarded(ctx, [&](Ctx &c) {
         QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v && energy, "(T): null argument");
         const long long O = o, V = v;
-        In t1(c, T1, O * V), t2(c, T2, O * O * V * V), g(c, oovv, O * O * V * V), w(c, vovv, V * O * V * V),
-                x(c, ovoo, O * V * O * O), eo(c, eps_o, O), ev(c, eps_v, V);
+        Trace tr(c, "qcp2_ccsd_t_range");
+        In t1(c, T1, O * V), t2(c, T2, O * O * V * V), g(c, oovv, O * O * V * V), x(c, ovoo, O * V * O * O), eo(c, eps_o, O),
+                ev(c, eps_v, V);
+        tr.mark("stage the small inputs");
+        TEval E;
+        bool done = false;
         int m = mode;
-        if (m == QCP2_T_AUTO) m = t_select_mode(c, t2, g, w, x, o, v);
-        std::unique_ptr<TPlan> plan(t_plan_create(c, t1, t2, g, w, x, eo, ev, o, v, m));
-        const long long nt = plan->ntriples;
-        DBuf et;
-        if (e_triples) {
-            et = DBuf(c, (size_t) std::max<long long>(nt, 1));
-            fill_zero(c, et, nt);
+        // host pointer mode, symmetric inputs: <vo||vv> is streamed -- H2D, b<c packing and the evaluation of the
+        // triples overlap, and the unpacked tensor never exists on the device
+        if (stream_allowed(c, mode, o, v) && (mode == QCP2_T_SYMMETRIC || t_select_mode(c, t2, g, nullptr, x, o, v) == QCP2_T_SYMMETRIC)) {
+            TStream ts;
+            ts.vovv_host = vovv;
+            t_evaluate(c, E, t1, t2, g, nullptr, x, eo, ev, o, v, QCP2_T_SYMMETRIC, &ts, first, stride, max_count, e_triples != nullptr, tr);
+            done = true;
+            if (mode == QCP2_T_AUTO) {// AUTO promised a check of <vo||vv> too: it ran slab by slab
+                double defect, mx;
+                t_plan_vovv_defect(*E.plan, &defect, &mx);
+                if (!(defect <= 1e-10 * mx)) done = false, m = QCP2_T_LITERAL, E = TEval();
+            }
         }
-        t_plan_run(*plan, first, stride, max_count, e_triples ? et.p : nullptr, energy);
+        In w;
+        if (!done) {
+            w = In(c, vovv, V * O * V * V);
+            tr.mark("stage <vo||vv> (H2D in host pointer mode)");
+            if (m == QCP2_T_AUTO) m = t_select_mode(c, t2, g, w, x, o, v);
+            tr.mark("select mode");
+            t_evaluate(c, E, t1, t2, g, w, x, eo, ev, o, v, m, nullptr, first, stride, max_count, e_triples != nullptr, tr);
+        }
+        *energy = E.partial;
+        const long long nt = E.nt;
         if (e_triples && nt > 0) {
             // only the evaluated entries are written back; the rest of e_triples is left untouched
             std::vector<double> h((size_t) nt);
-            QCP2_CUDA(cudaMemcpyAsync(h.data(), et.p, (size_t) nt * 8, cudaMemcpyDeviceToHost, c.stream));
+            QCP2_CUDA(cudaMemcpyAsync(h.data(), E.et.p, (size_t) nt * 8, cudaMemcpyDeviceToHost, c.stream));
             c.sync();
             long long cnt = first < nt ? (nt - first + stride - 1) / stride : 0;
             if (max_count >= 0) cnt = std::min(cnt, max_count);
@@ -497,6 +571,159 @@ int qcp2_ccsd_t(qcp2_ctx *ctx, const double *T1, const double *T2, const double 
                 const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
                 double *energy) {
     return qcp2_ccsd_t_range(ctx, T1, T2, oovv, vovv, ovoo, eps_o, eps_v, o, v, mode, 0, 1, -1, nullptr, energy);
+}
+
+/* ---- multi-GPU (one rank per GPU) --------------------------------------------------- */
+int qcp2_comm_get_unique_id(void *id, int id_bytes) {
+    if (!id || id_bytes < QCP2_COMM_ID_BYTES) return 2;
+    try {
+        comm_unique_id(id);
+        return 0;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "qcp2_comm_get_unique_id: %s\n", e.what());
+        return 1;
+    }
+}
+
+int qcp2_comm_init(qcp2_ctx *ctx, const void *id, int nranks, int rank) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(!ctx->comm, "comm_init: the context already has a communicator");
+        ctx->comm = comm_init(c, id, nranks, rank);
+    });
+}
+
+int qcp2_comm_destroy(qcp2_ctx *ctx) {
+    return guarded(ctx, [&](Ctx &c) {
+        c.sync();
+        comm_destroy(ctx->comm);
+        ctx->comm = nullptr;
+    });
+}
+
+int qcp2_comm_rank(const qcp2_ctx *ctx, int *rank, int *nranks) {
+    if (!ctx) return 2;
+    if (rank) *rank = ctx->comm ? ctx->comm->rank : 0;
+    if (nranks) *nranks = ctx->comm ? ctx->comm->nranks : 1;
+    return 0;
+}
+
+int qcp2_comm_broadcast(qcp2_ctx *ctx, double *dev_buf, long long n, int root) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(dev_buf || n == 0, "comm_broadcast: null buffer");
+        if (ctx->comm) comm_broadcast(c, *ctx->comm, dev_buf, n, root);
+    });
+}
+
+int qcp2_comm_allreduce_sum(qcp2_ctx *ctx, double *dev_buf, long long n) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(dev_buf || n == 0, "comm_allreduce_sum: null buffer");
+        if (ctx->comm) comm_allreduce_sum(c, *ctx->comm, dev_buf, n);
+    });
+}
+
+int qcp2_comm_allgather(qcp2_ctx *ctx, const double *dev_send, double *dev_recv, long long n_per_rank) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE((dev_send && dev_recv) || n_per_rank == 0, "comm_allgather: null buffer");
+        Comm single;
+        comm_allgather(c, ctx->comm ? *ctx->comm : single, dev_send, dev_recv, n_per_rank);
+    });
+}
+
+int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
+                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode, int root,
+                     double *e_triples, double *energy) {
+    return guarded(ctx, [&](Ctx &c) {
+        Comm single;
+        Comm &cm = ctx->comm ? *ctx->comm : single;
+        QCP2_REQUIRE(energy && o >= 0 && v >= 0, "(T) mgpu: null argument");
+        QCP2_REQUIRE(root >= 0 && root < cm.nranks, "(T) mgpu: root out of range");
+        const bool is_root = cm.rank == root;
+        if (is_root) QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v, "(T) mgpu: the root rank must supply every tensor");
+        Trace tr(c, "qcp2_ccsd_t_mgpu");
+        const long long O = o, V = v;
+        enum { kT1, kT2, kG, kW, kX, kEo, kEv };
+        const long long sizes[7] = {O * V, O * O * V * V, O * O * V * V, V * O * V * V, O * V * O * O, O, V};
+        const double *src[7] = {T1, T2, oovv, vovv, ovoo, eps_o, eps_v};
+        // device images: the root stages (HOST mode) or uses in place (DEVICE mode) its tensors; the other
+        // ranks receive into caller-provided device buffers (DEVICE mode) or scratch.  <vo||vv> is decided below.
+        DBuf scratch[7];
+        In staged[7];
+        double *dev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        auto place = [&](int k) {
+            if (is_root) {
+                staged[k] = In(c, src[k], sizes[k]);
+                dev[k] = const_cast<double *>(staged[k].p);
+            } else if (c.pointer_mode == QCP2_DEVICE && src[k]) {
+                dev[k] = const_cast<double *>(src[k]);
+            } else {
+                scratch[k] = DBuf(c, (size_t) std::max<long long>(sizes[k], 1));
+                dev[k] = scratch[k].p;
+            }
+        };
+        for (int k = 0; k < 7; ++k)
+            if (k != kW) place(k);
+        // header from the root: [0] evaluation mode, [1] 1 = <vo||vv> is streamed from the root's host tensor.
+        // The root's pointer mode decides (the other ranks may be in either mode).
+        DBuf hdr(c, 2);
+        double hh[2] = {0.0, 0.0};
+        if (is_root) {
+            int m = mode;
+            bool streamed = false;
+            if (stream_allowed(c, mode, o, v) &&
+                (mode == QCP2_T_SYMMETRIC || t_select_mode(c, dev[kT2], dev[kG], nullptr, dev[kX], o, v) == QCP2_T_SYMMETRIC))
+                streamed = true, m = QCP2_T_SYMMETRIC;
+            if (!streamed) {
+                place(kW);
+                if (m == QCP2_T_AUTO) m = t_select_mode(c, dev[kT2], dev[kG], dev[kW], dev[kX], o, v);
+            }
+            hh[0] = (double) m, hh[1] = streamed ? 1.0 : 0.0;
+            QCP2_CUDA(cudaMemcpyAsync(hdr.p, hh, 16, cudaMemcpyHostToDevice, c.stream));
+            c.sync();
+        }
+        comm_broadcast(c, cm, hdr.p, 2, root);
+        for (int k = 0; k < 7; ++k)
+            if (k != kW) comm_broadcast(c, cm, dev[k], sizes[k], root);
+        QCP2_CUDA(cudaMemcpyAsync(hh, hdr.p, 16, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        tr.mark("stage + broadcast the small inputs");
+        int m = (int) hh[0];
+        bool streamed = hh[1] != 0.0;
+        QCP2_REQUIRE(m == QCP2_T_LITERAL || m == QCP2_T_SYMMETRIC, "(T) mgpu: mode broadcast failed");
+        TEval E;
+        bool done = false;
+        if (streamed) {
+            TStream ts;
+            ts.vovv_host = is_root ? vovv : nullptr, ts.comm = &cm, ts.root = root;
+            t_evaluate(c, E, dev[kT1], dev[kT2], dev[kG], nullptr, dev[kX], dev[kEo], dev[kEv], o, v, QCP2_T_SYMMETRIC, &ts, cm.rank,
+                       cm.nranks, -1, true, tr);
+            done = true;
+            if (mode == QCP2_T_AUTO) {// the slab-wise <vo||vv> check, known to every rank through the broadcast
+                double defect, mx;
+                t_plan_vovv_defect(*E.plan, &defect, &mx);
+                if (!(defect <= 1e-10 * mx)) done = false, m = QCP2_T_LITERAL, E = TEval();
+            }
+        }
+        if (!done) {
+            if (!dev[kW]) place(kW);
+            comm_broadcast(c, cm, dev[kW], sizes[kW], root);
+            tr.mark("stage + broadcast <vo||vv>");
+            t_evaluate(c, E, dev[kT1], dev[kT2], dev[kG], dev[kW], dev[kX], dev[kEo], dev[kEv], o, v, m, nullptr, cm.rank, cm.nranks, -1,
+                       true, tr);// static round-robin: rank r owns r, r+W, ...
+        }
+        const long long nt = E.nt;
+        // every slot is written by exactly one rank, so the sum is exact (x + 0 + ... + 0) and the
+        // fixed-order host sum below is bit-identical for any number of ranks
+        comm_allreduce_sum(c, cm, E.et.p, nt);
+        std::vector<double> h((size_t) std::max<long long>(nt, 1), 0.0);
+        if (nt > 0) QCP2_CUDA(cudaMemcpyAsync(h.data(), E.et.p, (size_t) nt * 8, cudaMemcpyDeviceToHost, c.stream));
+        c.sync();
+        tr.mark("all-reduce + read back");
+        double total = 0.0;
+        for (long long t = 0; t < nt; ++t) total += h[(size_t) t];
+        if (e_triples)
+            for (long long t = 0; t < nt; ++t) e_triples[t] = h[(size_t) t];
+        *energy = total;
+    });
 }
 
 int qcp2_t_plan_create(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,

@@ -1,0 +1,23 @@
+// comm.cuh -- NCCL communicator of a context (one process / rank per GPU, NVLink 5 / NVSwitch).
+// NCCL is bound at run time (dlopen of libnccl.so.2), so the library has no link-time
+// dependency on it and shares the NCCL a host process may already have loaded.
+#pragma once
+#include "common.cuh"
+
+namespace qcp2 {
+
+struct Comm {
+    void *nccl = nullptr;// ncclComm_t
+    int rank = 0, nranks = 1;
+};
+
+void comm_unique_id(void *id128);
+Comm *comm_init(Ctx &ctx, const void *id128, int nranks, int rank);
+void comm_destroy(Comm *comm);
+// stream-ordered collectives on device buffers of doubles / raw bytes
+void comm_broadcast(Ctx &ctx, Comm &comm, double *buf, long long n, int root);
+void comm_broadcast_bytes(Ctx &ctx, Comm &comm, void *buf, long long nbytes, int root);
+void comm_allreduce_sum(Ctx &ctx, Comm &comm, double *buf, long long n);
+void comm_allgather(Ctx &ctx, Comm &comm, const double *send, double *recv, long long n_per_rank);
+
+}// namespace qcp2

@@ -164,11 +164,48 @@ void fill_zero(Ctx &ctx, double *p, long long n) {
     if (n > 0) QCP2_CUDA(cudaMemsetAsync(p, 0, (size_t) n * sizeof(double), ctx.stream));
 }
 
-// integrals.cpp:136-167 as a gather.  One block per (i,j) row pair, threads sweep (k,l) with l
-// fastest: writes are fully coalesced, reads walk rows of the spatial tensors (each value
-// serves two l's), all index arithmetic is 32-bit.
-__global__ void to_so_kernel(const double *__restrict__ aa, const double *__restrict__ bb,
-                             const double *__restrict__ ab, int n, double *__restrict__ so) {
+// integrals.cpp:136-167 as a gather.  One block per (i,j) row pair; a warp owns a row k and its
+// lanes sweep the spatial index L, each producing the adjacent pair (l = 2L, 2L+1) as one 16-byte
+// store: of the two spins of l exactly one can match, so a pair is (val, 0) or (0, val), and a
+// whole row is zero when the spin of k matches neither i nor j.  No integer division, reads walk
+// rows of the spatial tensors (contiguous in L), writes are fully coalesced.
+__global__ void __launch_bounds__(256) to_so_kernel(const double *__restrict__ aa, const double *__restrict__ bb,
+                                                    const double *__restrict__ ab, int n, double *__restrict__ so) {
+    const int n2 = 2 * n;
+    const int i = blockIdx.x / n2, j = blockIdx.x - i * n2;
+    const int si = i & 1, sj = j & 1, I = i >> 1, J = j >> 1;
+    double2 *out = reinterpret_cast<double2 *>(so + (size_t) blockIdx.x * n2 * n2);
+    const size_t n3 = (size_t) n * n * n, nn = (size_t) n * n;
+    const double *same = si ? bb : aa;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < n2; k += nwarps) {
+        const int sk = k & 1, K = k >> 1;
+        double2 *row = out + (size_t) k * n;
+        const double *p_ikj = nullptr, *p_jki = nullptr;// rows [I,K,J,:] and [J,K,I,:]
+        int slot = 0;                                   // which element of the pair carries the value
+        double sign = 1.0;
+        if (si == sj) {
+            if (sk == si) p_ikj = same + I * n3 + K * nn + (size_t) J * n, p_jki = same + J * n3 + K * nn + (size_t) I * n, slot = si;// :143-149
+        } else if (sk == si) {
+            p_ikj = ab + I * n3 + K * nn + (size_t) J * n, slot = sj;                                                                  // :151-155
+        } else {
+            p_ikj = ab + J * n3 + K * nn + (size_t) I * n, slot = si, sign = -1.0;                                                     // :157-161
+        }
+        if (!p_ikj) {
+            for (int L = lane; L < n; L += 32) row[L] = make_double2(0.0, 0.0);// never-written spin patterns (zero-initialised in the reference)
+            continue;
+        }
+        for (int L = lane; L < n; L += 32) {
+            double val = p_ikj[L];
+            if (p_jki) val -= p_jki[L];
+            val *= sign;
+            row[L] = slot ? make_double2(0.0, val) : make_double2(val, 0.0);
+        }
+    }
+}
+// scalar form for output buffers that are not 16-byte aligned
+__global__ void to_so_scalar_kernel(const double *__restrict__ aa, const double *__restrict__ bb,
+                                    const double *__restrict__ ab, int n, double *__restrict__ so) {
     const int n2 = 2 * n;
     const int i = blockIdx.x / n2, j = blockIdx.x - i * n2;
     const int si = i & 1, sj = j & 1, I = i >> 1, J = j >> 1;
@@ -187,20 +224,34 @@ __global__ void to_so_kernel(const double *__restrict__ aa, const double *__rest
 }
 void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, double *so) {
     if (n <= 0) return;
-    to_so_kernel<<<4u * n * n, kBlock, 0, ctx.stream>>>(aa, bb, ab, n, so);
+    if ((reinterpret_cast<uintptr_t>(so) & 15) == 0) to_so_kernel<<<4u * n * n, kBlock, 0, ctx.stream>>>(aa, bb, ab, n, so);
+    else to_so_scalar_kernel<<<4u * n * n, kBlock, 0, ctx.stream>>>(aa, bb, ab, n, so);
     ctx.launched("to_so");
 }
 
-// integrals.cpp:184-207.  One block per (p,q) pair of the block's first two indices; threads copy
-// the contiguous-in-s rows of the (r,s) panel.
-__global__ void slice_kernel(const double *__restrict__ so, int n2, int e1, int e2, int e3, int m0, int m1, int m2, int m3,
-                             double *__restrict__ out) {
+// integrals.cpp:184-207.  blockIdx.x = (p,q) pair of the block's first two indices, blockIdx.y = a
+// chunk of kSliceRows rows r of the (r,s) panel.  A warp copies four rows at a time (four
+// independent loads in flight per lane before the first store), lanes sweep the contiguous s.
+constexpr int kSliceRows = 32;
+__global__ void __launch_bounds__(256) slice_kernel(const double *__restrict__ so, int n2, int e1, int e2, int e3, int m0,
+                                                    int m1, int m2, int m3, double *__restrict__ out) {
     const int p = blockIdx.x / e1, q = blockIdx.x - p * e1;
     const double *src = so + ((size_t) (p + m0) * n2 + (q + m1)) * n2 * n2 + (size_t) m2 * n2 + m3;
     double *dst = out + (size_t) blockIdx.x * e2 * e3;
-    for (int rs = threadIdx.x; rs < e2 * e3; rs += blockDim.x) {
-        const int r = rs / e3, s = rs - r * e3;
-        dst[rs] = src[r * n2 + s];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;// 8 warps x 4 rows = kSliceRows
+    const int r0 = blockIdx.y * kSliceRows + warp * 4;
+    if (r0 >= e2) return;
+    const int nr = min(4, e2 - r0);
+    const double *s0 = src + (size_t) r0 * n2;
+    double *d0 = dst + (size_t) r0 * e3;
+    if (nr == 4) {
+        for (int s = lane; s < e3; s += 32) {
+            const double a = s0[s], b = s0[n2 + s], c = s0[2 * n2 + s], d = s0[3 * n2 + s];
+            d0[s] = a, d0[e3 + s] = b, d0[2 * e3 + s] = c, d0[3 * e3 + s] = d;
+        }
+    } else {
+        for (int r = 0; r < nr; ++r)
+            for (int s = lane; s < e3; s += 32) d0[r * e3 + s] = s0[r * n2 + s];
     }
 }
 void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *spec, double *out) {
@@ -214,7 +265,8 @@ void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *s
     QCP2_REQUIRE(o + v <= n2, "slice_ints: o + v exceeds the spin-orbital count");
     const long long total = (long long) e[0] * e[1] * e[2] * e[3];
     if (total == 0) return;
-    slice_kernel<<<(unsigned) (e[0] * e[1]), kBlock, 0, ctx.stream>>>(so, n2, e[1], e[2], e[3], m[0], m[1], m[2], m[3], out);
+    const dim3 grid((unsigned) (e[0] * e[1]), (unsigned) ((e[2] + kSliceRows - 1) / kSliceRows));
+    slice_kernel<<<grid, 256, 0, ctx.stream>>>(so, n2, e[1], e[2], e[3], m[0], m[1], m[2], m[3], out);
     ctx.launched("slice");
 }
 

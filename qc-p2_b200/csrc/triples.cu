@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/qcp2_b200.h"
+#include "comm.cuh"
 #include "tensor_ops.cuh"
 #include "triples.cuh"
 
@@ -50,6 +51,38 @@ __global__ void pack_bc_kernel(const double *__restrict__ src, long long R0, lon
         const long long r1 = r % R1, r0 = r / R1;
         const long long row = swap01 ? r1 * R0 + r0 : r0 * R1 + r1;
         dst[row * np + pair_index(b, c, v)] = src[lin];
+    }
+}
+
+// one streamed slab: src[e][b][c] (v^3 doubles, unpacked) -> dst[e][p(b<c)], and the antisymmetry
+// defect max |x[e,b,c] + x[e,c,b]| / max |x| of the slab accumulated into res[0..1]
+__global__ void pack_slab_kernel(const double *__restrict__ src, int v, double *__restrict__ dst,
+                                 unsigned long long *__restrict__ res) {
+    const long long np = (long long) v * (v - 1) / 2, n = (long long) v * v * v;
+    double defect = 0.0, mx = 0.0;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        const long long c = r % v;
+        r /= v;
+        const long long b = r % v, e = r / v;
+        if (b > c) continue;
+        const double x = src[lin];
+        if (b == c) {
+            defect = fmax(defect, fabs(2.0 * x)), mx = fmax(mx, fabs(x));
+            continue;
+        }
+        const double y = src[(e * v + c) * v + b];
+        defect = fmax(defect, fabs(x + y)), mx = fmax(mx, fmax(fabs(x), fabs(y)));
+        dst[e * np + pair_index(b, c, v)] = x;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        defect = fmax(defect, __shfl_xor_sync(0xffffffffu, defect, s));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    }
+    if ((threadIdx.x & 31) == 0) {// non-negative doubles order like their bit patterns
+        atomicMax(res, (unsigned long long) __double_as_longlong(defect));
+        atomicMax(res + 1, (unsigned long long) __double_as_longlong(mx));
     }
 }
 
@@ -380,16 +413,21 @@ int t_select_mode(Ctx &ctx, const double *T2, const double *oovv, const double *
         antisymmetry_defect(ctx, x, d0, d1, d2, d3, pair, &d, &m);
         return d <= tol * m;
     };
+    // vovv == nullptr: the caller checks <vo||vv> itself (streamed plans do it slab by slab)
     const bool sym = ok(T2, o, o, v, v, 0) && ok(T2, o, o, v, v, 1) && ok(oovv, o, o, v, v, 0) &&
-                     ok(oovv, o, o, v, v, 1) && ok(vovv, v, o, v, v, 1) && ok(ovoo, o, v, o, o, 1);
+                     ok(oovv, o, o, v, v, 1) && (!vovv || ok(vovv, v, o, v, v, 1)) && ok(ovoo, o, v, o, o, 1);
     return sym ? QCP2_T_SYMMETRIC : QCP2_T_LITERAL;
 }
 
 TPlan::~TPlan() {
     if (ctx) {
+        if (copy) cudaStreamSynchronize(copy);
         cudaStreamSynchronize(ctx->stream);
         if (aux) cudaStreamSynchronize(aux);
     }
+    for (cudaEvent_t e : slab_ready) cudaEventDestroy(e);
+    if (vovv_defect) cudaFree(vovv_defect);
+    if (copy) cudaStreamDestroy(copy);
     for (int s = 0; s < 2; ++s) {
         if (gemm_done[s]) cudaEventDestroy(gemm_done[s]);
         if (energy_done[s]) cudaEventDestroy(energy_done[s]);
@@ -404,8 +442,11 @@ TPlan::~TPlan() {
 }
 
 TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
-                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode) {
+                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
+                     const TStream *ts) {
     QCP2_REQUIRE(mode == QCP2_T_LITERAL || mode == QCP2_T_SYMMETRIC, "(T): mode must be LITERAL or SYMMETRIC");
+    QCP2_REQUIRE((vovv != nullptr) != (ts != nullptr), "(T): give either a device vovv or a stream source");
+    if (ts) QCP2_REQUIRE(mode == QCP2_T_SYMMETRIC && v >= 2, "(T): streamed <vo||vv> needs SYMMETRIC mode");
     QCP2_REQUIRE(o >= 1 && v >= 1, "(T): o and v must be positive");
     std::unique_ptr<TPlan> P(new TPlan());
     P->ctx = &ctx, P->o = o, P->v = v, P->mode = mode;
@@ -430,9 +471,64 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
                                                                                                    v, dst);
             ctx.launched("pack_bc");
         };
-        pack(vovv, V, O, 1, P->vovvP);// [e][i][b][c] -> [i][e][p]
+        if (!ts) pack(vovv, V, O, 1, P->vovvP);// [e][i][b][c] -> [i][e][p]
         pack(T2, O, O, 0, P->T2P);    // [i][m][b][c] -> [i][m][p]
         pack(oovv, O, O, 0, P->oovvP);
+        if (ts) {
+            const bool multi = ts->comm && ts->comm->nranks > 1;
+            const bool is_root = !multi || ts->comm->rank == ts->root;
+            if (is_root) QCP2_REQUIRE(ts->vovv_host != nullptr, "(T): the root rank must supply the host <vo||vv>");
+            {// highest priority: the short pack / broadcast kernels must not queue behind the GEMM's CTAs
+                int least = 0, greatest = 0;
+                QCP2_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+                QCP2_CUDA(cudaStreamCreateWithPriority(&P->copy, cudaStreamNonBlocking, greatest));
+            }
+            QCP2_CUDA(cudaMalloc(&P->vovv_defect, 16));
+            QCP2_CUDA(cudaMemsetAsync(P->vovv_defect, 0, 16, ctx.stream));
+            if (is_root) P->stage = DBuf(ctx, (size_t) (V * V * V));
+            // the copy stream starts once the stream-ordered allocations above exist
+            cudaEvent_t born;
+            QCP2_CUDA(cudaEventCreateWithFlags(&born, cudaEventDisableTiming));
+            QCP2_CUDA(cudaEventRecord(born, ctx.stream));
+            QCP2_CUDA(cudaStreamWaitEvent(P->copy, born, 0));
+            cudaStream_t main_stream = ctx.stream;
+            for (long long i = 0; i < O; ++i) {
+                double *slabP = P->vovvP.p + i * V * np;
+                if (is_root) {
+                    // vovv[e][i][b][c]: v rows of v^2 doubles, o*v^2 apart -> stage[e][b][c]
+                    QCP2_CUDA(cudaMemcpy2DAsync(P->stage.p, (size_t) (V * V) * 8, ts->vovv_host + i * V * V, (size_t) (O * V * V) * 8,
+                                                (size_t) (V * V) * 8, (size_t) V, cudaMemcpyHostToDevice, P->copy));
+                    pack_slab_kernel<<<grid_for(V * V * V, kBlock, ctx.sm_count, 4), kBlock, 0, P->copy>>>(P->stage.p, v, slabP,
+                                                                                                         P->vovv_defect);
+                    ctx.launched("pack_slab");
+                }
+                if (multi) {
+                    ctx.stream = P->copy;// enqueue the collective on the copy stream
+                    try {
+                        comm_broadcast(ctx, *ts->comm, slabP, V * np, ts->root);
+                    } catch (...) {
+                        ctx.stream = main_stream;
+                        throw;
+                    }
+                    ctx.stream = main_stream;
+                }
+                cudaEvent_t ready;
+                QCP2_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+                QCP2_CUDA(cudaEventRecord(ready, P->copy));
+                P->slab_ready.push_back(ready);
+            }
+            if (multi) {// every rank learns the root's verdict on the (b,c) antisymmetry
+                ctx.stream = P->copy;
+                try {
+                    comm_broadcast_bytes(ctx, *ts->comm, P->vovv_defect, 16, ts->root);
+                } catch (...) {
+                    ctx.stream = main_stream;
+                    throw;
+                }
+                ctx.stream = main_stream;
+            }
+            cudaEventDestroy(born);
+        }
     }
     // batch size: enough CTAs for ~48 full waves, bounded by a 4 GB X buffer
     const long long tiles = ((V + TileT::kBM - 1) / TileT::kBM) * ((std::max<long long>(P->ncols, 1) + TileT::kBN - 1) / TileT::kBN);
@@ -481,6 +577,16 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     return P.release();
 }
 
+void t_plan_vovv_defect(TPlan &P, double *defect, double *maxabs) {
+    QCP2_REQUIRE(P.copy && P.vovv_defect, "(T): not a streamed plan");
+    QCP2_CUDA(cudaStreamSynchronize(P.copy));
+    unsigned long long h[2];
+    QCP2_CUDA(cudaMemcpy(h, P.vovv_defect, 16, cudaMemcpyDeviceToHost));
+    long long b0 = (long long) h[0], b1 = (long long) h[1];
+    memcpy(defect, &b0, 8);
+    memcpy(maxabs, &b1, 8);
+}
+
 static void triple_of(long long t, int o, bool sym, int *ijk) {
     if (!sym) {
         ijk[2] = (int) (t % o), ijk[1] = (int) ((t / o) % o), ijk[0] = (int) (t / ((long long) o * o));
@@ -525,9 +631,26 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
     std::vector<int> ijk((size_t) (3 * count));
     std::vector<SegDesc> seg((size_t) count);
     std::vector<long long> gidx((size_t) count);
+    // processing order: the enumeration's own, except for streamed plans, which visit the triples by
+    // ascending largest occupied index so that work exists as soon as the first slabs have arrived
+    std::vector<long long> order((size_t) count);
+    for (long long q = 0; q < count; ++q) order[(size_t) q] = first + q * stride;
+    const bool streamed = !P.slab_ready.empty();
+    if (streamed) {
+        std::vector<int> key((size_t) (3 * count));
+        std::vector<long long> pos((size_t) count);
+        for (long long q = 0; q < count; ++q) triple_of(order[(size_t) q], P.o, sym, &key[(size_t) (3 * q)]), pos[(size_t) q] = q;
+        std::stable_sort(pos.begin(), pos.end(), [&](long long a, long long b) {
+            const int *x = &key[(size_t) (3 * a)], *y = &key[(size_t) (3 * b)];
+            return x[2] != y[2] ? x[2] < y[2] : (x[1] != y[1] ? x[1] < y[1] : x[0] < y[0]);
+        });
+        std::vector<long long> sorted((size_t) count);
+        for (long long q = 0; q < count; ++q) sorted[(size_t) q] = order[(size_t) pos[(size_t) q]];
+        order.swap(sorted);
+    }
     bool aligned = true;
     for (long long q = 0; q < count; ++q) {
-        const long long t = first + q * stride;
+        const long long t = order[(size_t) q];
         gidx[(size_t) q] = t;
         int *x = &ijk[(size_t) (3 * q)];
         triple_of(t, P.o, sym, x);
@@ -566,6 +689,11 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         const long long off = bq * P.tb;
         const int cnt = (int) std::min<long long>(P.tb, count - off);
         if (bq >= 2) QCP2_CUDA(cudaStreamWaitEvent(ctx.stream, P.energy_done[s], 0));
+        if (streamed) {// the batch's B rows: slabs up to its largest occupied index (the copy stream is in order)
+            int kmax = 0;
+            for (int q = 0; q < cnt; ++q) kmax = std::max(kmax, ijk[(size_t) (3 * (off + q) + 2)]);
+            QCP2_CUDA(cudaStreamWaitEvent(ctx.stream, P.slab_ready[(size_t) kmax], 0));
+        }
         BuildAArgs ba;
         ba.T2 = P.T2, ba.ovoo = P.ovoo, ba.ijk = P.ijk_dev + 3 * off, ba.A = P.Abuf[s];
         ba.o = P.o, ba.v = P.v, ba.kpad = P.kpad, ba.count = cnt;
@@ -638,8 +766,15 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
     QCP2_CUDA(cudaMemcpyAsync(e_host.data(), e_run.p, (size_t) count * 8, cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
     ctx.free(gidx_dev);
-    double tot = 0.0;
-    for (double x : e_host) tot += x;// fixed order: independent of batching and of the rank count
+    double tot = 0.0;// summed in the enumeration's order: independent of batching, scheduling and the rank count
+    if (streamed) {
+        std::vector<long long> by_index((size_t) count);
+        for (long long q = 0; q < count; ++q) by_index[(size_t) q] = q;
+        std::sort(by_index.begin(), by_index.end(), [&](long long a, long long b) { return gidx[(size_t) a] < gidx[(size_t) b]; });
+        for (long long q : by_index) tot += e_host[(size_t) q];
+    } else {
+        for (double x : e_host) tot += x;
+    }
     *energy_host = tot;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, P.t_begin, P.t_end);

@@ -51,13 +51,33 @@ struct TPlan {
     int blocks_per_triple = 0;
     int sym_items = 0;              // work items (a, bt <= ct) of the symmetric energy sweep
     int *items_dev = nullptr;
+    // streamed <vo||vv> (host-buffer entry points): the unpacked tensor never exists on the device; slab
+    // vovv[:,i,:,:] is copied H2D into `stage`, packed into vovvP[i] (and, with a communicator, broadcast)
+    // on the `copy` stream while the triples whose slabs have arrived are already being evaluated
+    cudaStream_t copy = nullptr;
+    std::vector<cudaEvent_t> slab_ready;  // one per occupied index
+    DBuf stage;
+    unsigned long long *vovv_defect = nullptr;// device [2]: max |x[e,b,c] + x[e,c,b]|, max |x| over the slabs
     bool use_tma = false;           // symmetric mode with 16-byte aligned packed rows
     long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
     ~TPlan();
 };
 
+struct Comm;
+// where a streamed plan gets <vo||vv> from: the root rank's HOST tensor [v][o][v][v] (null on the
+// other ranks), broadcast slab by slab when a communicator with more than one rank is given
+struct TStream {
+    const double *vovv_host = nullptr;
+    Comm *comm = nullptr;
+    int root = 0;
+};
+// vovv is a device pointer, or null together with a TStream (SYMMETRIC mode only)
 TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
-                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode);
+                     const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
+                     const TStream *ts = nullptr);
+// streamed plans: waits for the last slab and returns the antisymmetry defect of vovv in (b,c) seen by
+// the rank that packed it (after a broadcast: by every rank)
+void t_plan_vovv_defect(TPlan &plan, double *defect, double *maxabs);
 // evaluates triples first, first+stride, ... (< ntriples, at most max_count of them);
 // e_triples_dev (device, ntriples doubles, may be null) receives each triple's weighted
 // contribution at its global index; returns the partial sum in *energy_host.

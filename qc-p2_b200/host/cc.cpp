@@ -167,8 +167,21 @@ real_t CCSD_T(const cc_results &cc, const moes &m) {// cc.cpp:454-560
     for (int a = 0; a < v; ++a) ev[(size_t) a] = m.F_aa(a, a);
     real_t e = 0.0;
     const int_struct &I = cc.sliced_ints;
-    gpu_check(qcp2_ccsd_t(gpu(), cc.T1.data(), cc.T2.data(), I.oovv.data(), I.vovv.data(), I.ovoo.data(), eo.data(), ev.data(), o, v,
-                          QCP2_T_AUTO, &e));
+    if (mgpu().world > 1) {
+        // `P2 --gpus N`: the workers join through their pipes; tensors are replicated by ncclBroadcast from this
+        // rank, triples dealt round-robin, one ncclAllReduce -- same energy, bit for bit
+        MgpuCommand cmd;
+        cmd.cmd = 1, cmd.o = o, cmd.v = v;
+        if (qcp2_comm_get_unique_id(cmd.id, QCP2_COMM_ID_BYTES) != 0) throw std::runtime_error("qcp2_b200: NCCL is not available");
+        mgpu_send(cmd);
+        gpu_check(qcp2_comm_init(gpu(), cmd.id, mgpu().world, 0));
+        gpu_check(qcp2_ccsd_t_mgpu(gpu(), cc.T1.data(), cc.T2.data(), I.oovv.data(), I.vovv.data(), I.ovoo.data(), eo.data(), ev.data(),
+                                   o, v, QCP2_T_AUTO, 0, nullptr, &e));
+        gpu_check(qcp2_comm_destroy(gpu()));
+    } else {
+        gpu_check(qcp2_ccsd_t(gpu(), cc.T1.data(), cc.T2.data(), I.oovv.data(), I.vovv.data(), I.ovoo.data(), eo.data(), ev.data(), o, v,
+                              QCP2_T_AUTO, &e));
+    }
     std::cout << "(T) energy: " << e << " Eh" << std::endl;
     return e;
 }

@@ -4,6 +4,7 @@
 // (12 digits on a -76 Eh total are too coarse to assert 1e-10).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <iomanip>
 #include <iostream>
 
@@ -19,11 +20,24 @@ int main(int argc, char *argv[]) {
     // `P2 --fused <input.json>`: same inputs and outputs, but MP2 -> CCSD -> (T) run as ONE device-
     // resident call (qcp2_post_hf) instead of the reference's function-by-function sequence, which
     // moves so_ints / sliced integrals through host memory between the stages.
+    // `P2 --gpus N <input.json>`: N processes, one per GPU (forked here, before any CUDA / OpenMP
+    // state exists); rank 0 runs the program below, the others join the (T) stage over NCCL.
     bool fused = false;
-    if (argc >= 2 && std::string(argv[1]) == "--fused") fused = true, --argc, ++argv;
-    if (argc < 2) {
-        std::cerr << "usage: P2 [--fused] <input.json>" << endl;
+    int gpus = 1;
+    for (;;) {
+        if (argc >= 2 && std::string(argv[1]) == "--fused") fused = true, --argc, ++argv;
+        else if (argc >= 3 && std::string(argv[1]) == "--gpus") gpus = std::atoi(argv[2]), argc -= 2, argv += 2;
+        else break;
+    }
+    if (argc < 2 || gpus < 1 || (fused && gpus > 1)) {
+        std::cerr << "usage: P2 [--fused | --gpus N] <input.json>" << endl;
         return 2;
+    }
+    try {
+        mgpu_spawn(gpus);
+    } catch (const std::exception &e) {
+        std::cerr << "P2: " << e.what() << endl;
+        return 1;
     }
     cout << std::setprecision(12);
     try {
@@ -68,7 +82,7 @@ int main(int argc, char *argv[]) {
                 cout << "Total energy: " << e_scf + (stages >= 2 ? e_cc : e_mp2) + e_t << " Eh" << endl;
                 printf("RESULT {\"e_scf\": %.17g, \"e_mp2\": %.17g, \"e_ccsd\": %.17g, \"e_t\": %.17g}\n", e_scf, e_mp2, e_cc, e_t);
                 gpu_release();
-                return 0;
+                return mgpu_shutdown();
             }
             auto mp2 = MP2(obs, hf, config, &ao);
             e_mp2 = mp2.energy;
@@ -90,8 +104,9 @@ int main(int argc, char *argv[]) {
     } catch (const std::exception &e) {
         std::cerr << "P2: " << e.what() << endl;
         gpu_release();
+        mgpu_shutdown();
         return 1;
     }
     gpu_release();
-    return 0;
+    return mgpu_shutdown();
 }

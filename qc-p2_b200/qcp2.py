@@ -23,6 +23,7 @@ INT_NAMES = ["oooo", "ovoo", "oovo", "ooov", "ovov", "ovvo", "oovv", "vovv", "ov
 INTER_NAMES = ["F_ae", "F_mi", "F_me", "W_mnij", "W_mbej", "W_abef"]
 HOST, DEVICE = 0, 1
 T_AUTO, T_LITERAL, T_SYMMETRIC = 0, 1, 2
+COMM_ID_BYTES = 128
 
 _lib = None
 PD = C.POINTER(C.c_double)
@@ -46,6 +47,14 @@ def load_library():
         lib.qcp2_ccsd_last_loop_seconds.restype = C.c_double
         _lib = lib
     return _lib
+
+
+def comm_unique_id():
+    """qcp2_comm_get_unique_id: the NCCL bootstrap id, created by rank 0 and handed to every rank."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    if load_library().qcp2_comm_get_unique_id(buf, COMM_ID_BYTES) != 0:
+        raise QCP2Error("qcp2_comm_get_unique_id failed (is NCCL available?)")
+    return buf.raw
 
 
 def inter_shapes(o, v):
@@ -291,6 +300,50 @@ class Context:
         if want_amplitudes:
             out.update(T1=T1, T2=T2)
         return out
+
+    # ---- multi-GPU: NCCL communicator owned by the library (one rank per GPU) ----------------
+    def comm_init(self, unique_id, nranks, rank):
+        """qcp2_comm_init: collective; unique_id = the 128 bytes rank 0 got from comm_unique_id()."""
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self.check(self.lib.qcp2_comm_init(self.h, buf, int(nranks), int(rank)))
+
+    def comm_init_from_torch(self, dist):
+        """Bootstrap the library's own NCCL communicator over an initialised torch.distributed group:
+        rank 0 creates the unique id, the host channel of the group hands it round."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], world, rank)
+
+    def comm_destroy(self):
+        self.check(self.lib.qcp2_comm_destroy(self.h))
+
+    def comm_rank(self):
+        r, n = C.c_int(), C.c_int()
+        self.lib.qcp2_comm_rank(self.h, C.byref(r), C.byref(n))
+        return r.value, n.value
+
+    def comm_broadcast(self, dev_tensor, root=0):
+        self.check(self.lib.qcp2_comm_broadcast(self.h, _p(dev_tensor), C.c_longlong(dev_tensor.numel()), int(root)))
+
+    def comm_allreduce_sum(self, dev_tensor):
+        self.check(self.lib.qcp2_comm_allreduce_sum(self.h, _p(dev_tensor), C.c_longlong(dev_tensor.numel())))
+
+    def comm_allgather(self, dev_send, dev_recv):
+        self.check(self.lib.qcp2_comm_allgather(self.h, _p(dev_send), _p(dev_recv), C.c_longlong(dev_send.numel())))
+
+    def CCSD_T_mgpu(self, T1, T2, oovv, vovv, ovoo, eps_o, eps_v, o, v, mode=T_AUTO, root=0, want_triples=False):
+        """cc.cpp:454-560 across the communicator (qcp2_ccsd_t_mgpu): the root rank passes the tensors
+        (numpy in host pointer mode, torch CUDA tensors in device pointer mode), the others None."""
+        conv = (lambda a: a) if (T1 is not None and not isinstance(T1, np.ndarray)) else _arr
+        args = [conv(a) if a is not None else None for a in (T1, T2, oovv, vovv, ovoo, eps_o, eps_v)]
+        E = C.c_double()
+        et = np.zeros(max(self.t_count(o, T_SYMMETRIC if mode != T_LITERAL else T_LITERAL), 1)) if want_triples else None
+        if want_triples and mode == T_AUTO:
+            et = np.zeros(max(self.t_count(o, T_LITERAL), 1))  # large enough for either enumeration
+        self.check(self.lib.qcp2_ccsd_t_mgpu(self.h, *[_p(a) for a in args], int(o), int(v), int(mode), int(root),
+                                             _p(et), C.byref(E)))
+        return (E.value, et) if want_triples else E.value
 
     def t_count(self, o, mode):
         return int(self.lib.qcp2_ccsd_t_count(o, mode))

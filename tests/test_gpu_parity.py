@@ -334,3 +334,60 @@ def test_t_full_size_sampled_triples_and_device_plan():
     assert tm["gemm_launches"] >= 1 and tm["gemm_seconds"] > 0
     plan.close()
     ctx.close()
+
+
+def test_t_streamed_and_resident_vovv_paths_agree(ctx, monkeypatch):
+    """Host-pointer calls stream <vo||vv> slab by slab (H2D + packing overlapped with the triples, colex
+    schedule); QCP2_T_NO_STREAM=1 takes the resident path.  Same per-triple values and sums, bit for bit;
+    AUTO falls back to LITERAL when only <vo||vv> breaks the antisymmetry (caught by the slab-wise check)."""
+    o, v = 7, 30
+    s = npo.synthetic_t_inputs(o, v)
+    args = [s[k] for k in ("T1", "T2", "oovv", "vovv", "ovoo", "eps_o", "eps_v")]
+    nt = ctx.t_count(o, qcp2_b200.T_SYMMETRIC)
+    e_stream, e_res = np.zeros(nt), np.zeros(nt)
+    a = ctx.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, 0, 1, -1, e_stream)
+    b = ctx.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, 1, 3, 5, None)
+    monkeypatch.setenv("QCP2_T_NO_STREAM", "1")
+    a2 = ctx.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, 0, 1, -1, e_res)
+    b2 = ctx.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, 1, 3, 5, None)
+    monkeypatch.delenv("QCP2_T_NO_STREAM")
+    assert np.array_equal(e_stream, e_res) and a == a2 and b == b2
+    bad = [x.copy() for x in args]
+    bad[3][1, 2, 3, 4] += 0.25  # <vo||vv> no longer antisymmetric in (b,c); everything else still is
+    ref = orc.ccsd_t(bad[0], bad[1], bad[2], bad[3], bad[4], np.diag(bad[5]), np.diag(bad[6]))
+    got = ctx.CCSD_T(*bad, qcp2_b200.T_AUTO)
+    assert abs(got - ref) < 1e-12 * max(1.0, abs(ref))
+    assert abs(got - a) > 1e-8  # and it is a different number from the symmetric evaluation
+
+
+def test_t_mgpu_entry_point_on_a_single_rank_communicator():
+    """qcp2_ccsd_t_mgpu with the library's own NCCL communicator at world size 1 (what one GPU can
+    check; tools/mgpu_check.py does ranks 2..8 under torchrun): same energy and per-triple values as
+    qcp2_ccsd_t, bit for bit, in host and device pointer mode."""
+    import torch
+    c = qcp2_b200.Context(0)
+    c.comm_init(qcp2_b200.comm_unique_id(), 1, 0)
+    assert c.comm_rank() == (0, 1)
+    o, v = 6, 33
+    s = npo.synthetic_t_inputs(o, v)
+    names = ("T1", "T2", "oovv", "vovv", "ovoo", "eps_o", "eps_v")
+    args = tuple(s[k] for k in names)
+    e_tr = np.zeros(c.t_count(o, qcp2_b200.T_SYMMETRIC))
+    want = c.CCSD_T_range(*args, qcp2_b200.T_SYMMETRIC, 0, 1, -1, e_tr)
+    got, per = c.CCSD_T_mgpu(*args, o, v, qcp2_b200.T_AUTO, root=0, want_triples=True)
+    seq = 0.0
+    for x in e_tr.tolist():  # (the builtin sum() compensates since Python 3.12)
+        seq += x
+    assert got == seq == want and np.array_equal(per[:len(e_tr)], e_tr)
+    # device pointer mode + the collective building blocks
+    c.set_pointer_mode(qcp2_b200.DEVICE)
+    dev = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in args]
+    assert c.CCSD_T_mgpu(*dev, o, v, qcp2_b200.T_SYMMETRIC, root=0) == got
+    x = torch.arange(5, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    c.comm_broadcast(x, 0), c.comm_allreduce_sum(x), c.comm_allgather(x, y)
+    c.synchronize()
+    assert torch.equal(x.cpu(), torch.arange(5, dtype=torch.float64)) and torch.equal(x, y)
+    c.comm_destroy()
+    assert c.comm_rank() == (0, 1)
+    c.close()

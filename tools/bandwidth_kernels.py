@@ -18,8 +18,13 @@ HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if o
     os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
 
+ONCE = os.environ.get("QCP2_BW_ONCE") == "1"  # under ncu: one launch of each kernel is enough
+
+
 def timed(fn, reps=5):
     fn()
+    if ONCE:
+        return 1.0
     best = 1e9
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -54,6 +59,11 @@ def main():
         rows.append(r)
         print(r, flush=True)
 
+    # local ceilings for context: device-to-device copy (read + write) and pure write (memset) of 7 GB
+    big0, big1 = torch.empty(7 * 2 ** 27, **f), torch.empty(7 * 2 ** 27, **f)
+    rec("ceiling: torch copy_ 7.5 GB -> 7.5 GB", timed(lambda: big1.copy_(big0)), nbytes=16.0 * big0.numel())
+    rec("ceiling: torch zero_ 7.5 GB (write only)", timed(lambda: big1.zero_()), nbytes=8.0 * big0.numel())
+    del big0, big1
     ao, Cm = torch.randn((n,) * 4, **f), torch.randn((n, n), **f)
     mo = torch.empty((n,) * 4, **f)
     rec("transform_ao_mo n=86 (4 DMMA GEMMs)", timed(lambda: ctx.check(lib.qcp2_transform_ao_mo(h, p(ao), p(Cm), p(Cm), n, p(mo)))),

@@ -27,6 +27,23 @@ struct Error : std::runtime_error {
         if (!(cond)) throw ::qcp2::Error(std::string(msg)); \
     } while (0)
 
+// Re-layout cache (contract.cu): while it is installed, operand re-layouts of the tensors registered
+// as constant (the integral blocks inside the CCSD loop) are computed once and reused.
+struct PermCache {
+    struct Entry {
+        const double *src;
+        std::string sig;
+        double *buf;
+    };
+    std::vector<const double *> constants;
+    std::vector<Entry> entries;
+    bool is_constant(const double *p) const {
+        for (const double *c : constants)
+            if (c == p) return true;
+        return false;
+    }
+};
+
 // Execution context: one device, one stream, a stream-ordered workspace allocator and a
 // launch counter (bench.py reports it as gpu_launches).
 struct Ctx {
@@ -38,6 +55,7 @@ struct Ctx {
     long long launches = 0;
     std::string last_error;
     double ccsd_loop_seconds = 0.0;
+    PermCache *perm_cache = nullptr;
 
     double *alloc(size_t n_doubles) {
         void *p = nullptr;

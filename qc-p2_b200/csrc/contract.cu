@@ -102,6 +102,28 @@ void relayout(Ctx &ctx, double *dst, const double *src, const std::string &from,
     permute_axpby(ctx, dst, src, (int) to.size(), oext, istr, alpha, beta);
 }
 
+// operand re-layout of a (possibly batched) tensor, served from the context's cache when the source
+// is registered as constant; returns the buffer to feed to the GEMM
+const double *operand_relayout(Ctx &ctx, DBuf &tmp, const double *src, long long stride, int nb, const std::string &from,
+                               const long long *efrom, const std::string &to) {
+    const long long n = total(from, efrom);
+    PermCache *pc = ctx.perm_cache;
+    const bool cacheable = pc && pc->is_constant(src);
+    std::string sig;
+    if (cacheable) {
+        sig = from + ">" + to + ":" + std::to_string(nb) + ":" + std::to_string(stride);
+        for (size_t k = 0; k < from.size(); ++k) sig += "," + std::to_string(efrom[k]);
+        for (const PermCache::Entry &e : pc->entries)
+            if (e.src == src && e.sig == sig) return e.buf;
+    }
+    double *dst;
+    if (cacheable) dst = ctx.alloc((size_t) (n * nb));
+    else tmp = DBuf(ctx, (size_t) (n * nb)), dst = tmp.p;
+    for (int z = 0; z < nb; ++z) relayout(ctx, dst + z * n, src + z * stride, from, efrom, to, 1.0, 0.0);
+    if (cacheable) pc->entries.push_back(PermCache::Entry{src, sig, dst});
+    return dst;
+}
+
 void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, double *C, const Spec &s,
          const Plan &p, int batch, long long sA, long long sB, long long sC, const double *cin) {
     const long long M = prod(p.M, s.c, s.ec), N = prod(p.N, s.c, s.ec), K = prod(p.K, s.a, s.ea);
@@ -112,15 +134,13 @@ void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, 
     bool a_kc = p.a_kc, b_nc = p.b_nc;
     if (!p.a_direct) {// -> [M][K]
         const long long n = total(s.a, s.ea);
-        ta = DBuf(ctx, (size_t) (n * (sA ? batch : 1)));
-        for (int z = 0; z < (sA ? batch : 1); ++z) relayout(ctx, ta.p + z * n, A + z * sA, s.a, s.ea, p.M + p.K, 1.0, 0.0);
-        Ag = ta.p, a_kc = true, sAg = sA ? n : 0;
+        Ag = operand_relayout(ctx, ta, A, sA, sA ? batch : 1, s.a, s.ea, p.M + p.K);
+        a_kc = true, sAg = sA ? n : 0;
     }
     if (!p.b_direct) {// -> [K][N]
         const long long n = total(s.b, s.eb);
-        tb = DBuf(ctx, (size_t) (n * (sB ? batch : 1)));
-        for (int z = 0; z < (sB ? batch : 1); ++z) relayout(ctx, tb.p + z * n, B + z * sB, s.b, s.eb, p.K + p.N, 1.0, 0.0);
-        Bg = tb.p, b_nc = true, sBg = sB ? n : 0;
+        Bg = operand_relayout(ctx, tb, B, sB, sB ? batch : 1, s.b, s.eb, p.K + p.N);
+        b_nc = true, sBg = sB ? n : 0;
     }
     GemmArgs g;
     g.batch = batch;

@@ -53,8 +53,14 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
         const long long tiles = (long long) ((g.M + cand[t].bm - 1) / cand[t].bm) * ((g.N + cand[t].bn - 1) / cand[t].bn) * g.batch;
         const int cta_per_sm = cand[t].bm == 64 ? 2 : 1;
         const long long slots = (long long) ctx.sm_count * cta_per_sm;
-        for (int split = 1; split <= 64; split *= 2) {
-            if (split > 1 && (nkb / split < 4 || tiles * (split / 2) >= 4 * slots || t == 3)) break;
+        // split-K candidates: powers of two and the factors that fill exactly one wave (skinny products with a
+        // huge contracted dimension -- M, N <= a tile, K = o v^2 -- are bound by how many CTAs stream K)
+        int cands[16], nc = 0;
+        for (int split = 1; split <= 512; split *= 2) cands[nc++] = split;
+        if (tiles < slots) cands[nc++] = (int) (slots / tiles), cands[nc++] = (int) std::max<long long>(1, ctx.sm_count / tiles);
+        for (int q = 0; q < nc; ++q) {
+            const int split = cands[q];
+            if (split > 1 && (nkb / split < 4 || tiles * split > 4 * slots || t == 3)) continue;
             const long long ctas = tiles * split;
             const double waves = (double) ((ctas + slots - 1) / slots);
             const double conc = (double) std::min<long long>(cta_per_sm, (ctas + ctx.sm_count - 1) / ctx.sm_count);
@@ -66,6 +72,10 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     }
     DBuf ws;
     GemmArgs run = g;
+    if (best_split > 1) {// no empty splits: with the rounded-up k-blocks per split fewer splits may already cover K
+        const int per = (nkb + best_split - 1) / best_split;
+        best_split = (nkb + per - 1) / per;
+    }
     if (best_split > 1) {
         const long long mn = (long long) g.M * g.N;
         ws = DBuf(ctx, (size_t) (mn * best_split * g.batch));

@@ -105,13 +105,15 @@ void mp2_dev(Ctx &ctx, const double *ao, const double *Ca, const double *Cb, con
 void update_intermediates_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const double *foo,
                               const double *fov, const double *fvv, int o, int v, const InterDev &X) {
     const long long O = o, V = v, o2v2 = O * O * V * V;
+    const bool fused = X.p[X_WABEF] == nullptr;// the fused solver (ccsd_dev); the standalone entry point stays literal
     const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
     const TView oooo = int_view(I, I_OOOO, o, v), ooov = int_view(I, I_OOOV, o, v), oovo = int_view(I, I_OOVO, o, v),
                 oovv = int_view(I, I_OOVV, o, v), vovv = int_view(I, I_VOVV, o, v), ovvv = int_view(I, I_OVVV, o, v);
     DBuf taub(ctx, (size_t) o2v2), tau(ctx, (size_t) o2v2), tt(ctx, (size_t) o2v2);
     make_tau(ctx, Ts, Td, o, v, true, taub);
     make_tau(ctx, Ts, Td, o, v, false, tau);
-    multiply_Ts(ctx, Ts, o, v, tt);
+    if (fused) wmbej_amplitudes(ctx, Ts, Td, o, v, tt);// [j,b,n,f]
+    else multiply_Ts(ctx, Ts, o, v, tt);
     const TView vtaub(taub.p, {O, O, V, V}), vtau(tau.p, {O, O, V, V}), vtt(tt.p, {O, V, O, V});
 
     const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
@@ -144,8 +146,12 @@ void update_intermediates_dev(Ctx &ctx, const double *Ts, const double *Td, cons
 
     contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 1.0, Wmbej, "mbej", I.p[I_OVVO]);     // :245 (+ :250 <mb||ej> in the epilogue)
     contract(ctx, -1.0, ts, "nb", oovo, "mnej", 1.0, Wmbej, "mbej");                 // :246
-    contract(ctx, -0.5, td, "jnfb", oovv, "mnef", 1.0, Wmbej, "mbej");               // :247
-    contract(ctx, -1.0, vtt, "jfnb", oovv, "mnef", 1.0, Wmbej, "mbej");              // :249
+    if (fused) {// :247 + :249 share <mn||ef> and the target: one product with -(1/2 t_jnfb + t_jf t_nb)
+        contract(ctx, 1.0, TView(tt.p, {O, V, O, V}), "jbnf", oovv, "mnef", 1.0, Wmbej, "mbej");
+    } else {
+        contract(ctx, -0.5, td, "jnfb", oovv, "mnef", 1.0, Wmbej, "mbej");           // :247
+        contract(ctx, -1.0, vtt, "jfnb", oovv, "mnef", 1.0, Wmbej, "mbej");          // :249
+    }
 }
 
 // cc.cpp:257-292 -- Stanton eq. 1
@@ -300,6 +306,20 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
             pack.vvvvP = vvvvP.p, pack.pairs_o = pairs_dev;
         }
     }
+    // the integral blocks are constant for the whole loop: their operand re-layouts are made once
+    PermCache perm_cache;
+    for (int k = 0; k < I_COUNT; ++k)
+        if (I.p[k]) perm_cache.constants.push_back(I.p[k]);
+    struct CacheGuard {
+        Ctx &c;
+        PermCache &pc;
+        CacheGuard(Ctx &ctx_, PermCache &p) : c(ctx_), pc(p) { c.perm_cache = &pc; }
+        ~CacheGuard() {
+            c.perm_cache = nullptr;
+            for (PermCache::Entry &e : pc.entries) c.free(e.buf);
+        }
+    } cache_guard(ctx, perm_cache);
+    if (getenv("QCP2_CCSD_NO_PERM_CACHE")) ctx.perm_cache = nullptr;
     fill_zero(ctx, T1, O * V);                                                             // :417-419
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
     cudaEvent_t ev0, ev1;

@@ -431,6 +431,33 @@ __global__ void multiply_ts_kernel(const double *__restrict__ ts, int o, int v, 
     const long long n = (long long) o * v * o * v, ov = (long long) o * v;
     GRID_STRIDE(lin, n) out[lin] = ts[lin / ov] * ts[lin % ov];// out[j,f,n,b] = t[j,f] t[n,b]
 }
+// out[j,b,n,f] = -1/2 Td[j,n,f,b] - Ts[j,f] Ts[n,b]: the amplitude factor of the last two terms of
+// Stanton eq. 8 (cc.cpp:247 and :249 share <mn||ef> and the target), already in (free | contracted) order
+__global__ void wmbej_amp_kernel(const double *__restrict__ ts, const double *__restrict__ td, int o, int v,
+                                 double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    // one block = one (j, n) pair and a 32x32 (f, b) tile: Td[j,n,f,b] is read with b fastest, written with f fastest
+    const int jn = blockIdx.z, j = jn / o, n = jn - j * o;
+    const int f0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;// 32 x 8
+    const double *src = td + ((size_t) j * o + n) * v * v;
+    for (int r = ty; r < 32; r += 8) {
+        const int f = f0 + r, b = b0 + tx;
+        if (f < v && b < v) tile[r][tx] = -0.5 * src[(size_t) f * v + b] - ts[j * v + f] * ts[n * v + b];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int b = b0 + r, f = f0 + tx;
+        if (f < v && b < v) out[(((size_t) j * v + b) * o + n) * v + f] = tile[tx][r];
+    }
+}
+void wmbej_amplitudes(Ctx &ctx, const double *Ts, const double *Td, int o, int v, double *out) {
+    if (o <= 0 || v <= 0) return;
+    const dim3 grid((unsigned) ((v + 31) / 32), (unsigned) ((v + 31) / 32), (unsigned) (o * o));
+    wmbej_amp_kernel<<<grid, 256, 0, ctx.stream>>>(Ts, Td, o, v, out);
+    ctx.launched("wmbej_amplitudes");
+}
+
 void multiply_Ts(Ctx &ctx, const double *Ts, int o, int v, double *out) {
     const long long n = (long long) o * v * o * v;
     if (n == 0) return;

@@ -23,6 +23,8 @@ void make_fock(Ctx &ctx, const double *e1, const double *e2, int n1, int n2, dou
 // cc.cpp elementwise pieces
 void make_tau(Ctx &ctx, const double *Ts, const double *Td, int o, int v, bool bar, double *out);
 void multiply_Ts(Ctx &ctx, const double *Ts, int o, int v, double *out);
+// out[j,b,n,f] = -1/2 Td[j,n,f,b] - Ts[j,f] Ts[n,b]   (cc.cpp:247 + :249 as one operand)
+void wmbej_amplitudes(Ctx &ctx, const double *Ts, const double *Td, int o, int v, double *out);
 void add_offdiag(Ctx &ctx, double *F, const double *Fadd, int n);// F(a,e) += (1-d_ae) Fadd(a,e)
 void make_D_ia(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);
 void make_D_ijab(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);

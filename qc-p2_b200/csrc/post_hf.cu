@@ -5,6 +5,7 @@
 // cc.cpp line by line; the elementwise pieces are the kernels of tensor_ops.cu.
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "contract.cuh"
@@ -190,9 +191,26 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
             d2(ctx, (size_t) (O * O));
     const TView R(r.p, {O, O, V, V}), D1(d1.p, {V, V}), D2(d2.p, {O, O});
     make_tau(ctx, Ts, Td, o, v, false, tau);
-    multiply_Ts(ctx, Ts, o, v, tt);
+    if (Wabef.p) multiply_Ts(ctx, Ts, o, v, tt);// literal path only (cc.cpp:360-363)
     const TView vtau(tau.p, {O, O, V, V}), vtt(tt.p, {O, V, O, V});
 
+    const bool fused = Wabef.p == nullptr;// the fused solver; the standalone entry point keeps the literal term list
+    DBuf ubuf;
+    if (fused) ubuf = DBuf(ctx, (size_t) o2v2);
+    const TView U(ubuf.p, {O, O, V, V});
+    if (fused) {
+        // cc.cpp:316-328: P(ab) t_ijae (F_be - 1/2 t_mb F_me).  The (a<->b) partner of each product is the same
+        // product with two labels exchanged, and the two factors share t_ijae: ONE product + antisymmetrised add
+        contract(ctx, 1.0, ts, "mb", Fme, "me", 0.0, D1, "be");             // :322
+        axpby(ctx, d1.p, Fae.p, 1.0, -0.5, V * V);                          // F_be - 1/2 t_mb F_me
+        contract(ctx, 1.0, td, "ijae", D1, "be", 0.0, U, "ijab");           // :316 + :324
+        antisym_add(ctx, U.p, I.p[I_OOVV], o, v, 1, r);                     // + <ij||ab> (:312), - (a<->b) (:317 + :328)
+        // cc.cpp:333-343: -P(ij) t_imab (F_mj + 1/2 t_je F_me)
+        contract(ctx, 1.0, ts, "je", Fme, "me", 0.0, D2, "mj");             // :339 (stored as [m,j])
+        axpby(ctx, d2.p, Fmi.p, 1.0, 0.5, O * O);                           // F_mj + 1/2 t_je F_me
+        contract(ctx, -1.0, td, "imab", D2, "mj", 0.0, U, "ijab");          // :333 + :340
+        antisym_add(ctx, U.p, nullptr, o, v, 0, r);                         // - (i<->j) (:334 + :343)
+    } else {
     contract(ctx, 1.0, td, "ijae", Fae, "be", 1.0, R, "ijab", I.p[I_OOVV]);// :316 (+ :312 <ij||ab> in the epilogue)
     contract(ctx, -1.0, td, "ijbe", Fae, "ae", 1.0, R, "ijab");         // :317
     contract(ctx, 1.0, ts, "mb", Fme, "me", 0.0, D1, "be");             // :322
@@ -205,6 +223,7 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
     contract(ctx, -0.5, td, "imab", D2, "jm", 1.0, R, "ijab");          // :340
     contract(ctx, 1.0, ts, "ie", Fme, "me", 0.0, D2, "im");             // :341-342
     contract(ctx, 0.5, td, "jmab", D2, "im", 1.0, R, "ijab");           // :343
+    }
     contract(ctx, 0.5, vtau, "mnab", Wmnij, "mnij", 1.0, R, "ijab");    // :346
     if (Wabef.p) {
         contract(ctx, 0.5, vtau, "ijef", Wabef, "abef", 1.0, R, "ijab");// :348  particle-particle ladder
@@ -216,7 +235,9 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
         make_tau(ctx, Ts_old, Td, o, v, false, tau_old);
         const TView vtauo(tau_old.p, {O, O, V, V}), Y(y.p, {O, O, O, O}), Z(z.p, {O, O, V, O});
         bool packed = false;
-        if (pack && pack->vvvvP && pack->npo > 0 && pack->npv > 0) {// tau must be antisymmetric for the e<f / i<j restriction
+        if (pack && pack->vvvvP && pack->npo > 0 && pack->npv > 0 && pack->tau_antisymmetric >= 0) {
+            packed = pack->tau_antisymmetric != 0;
+        } else if (pack && pack->vvvvP && pack->npo > 0 && pack->npv > 0) {// tau must be antisymmetric for the e<f / i<j restriction
             double d0, d1, m0, m1;
             antisymmetry_defect(ctx, tau, O, O, V, V, 0, &d0, &m0);
             antisymmetry_defect(ctx, tau, O, O, V, V, 1, &d1, &m1);
@@ -254,16 +275,29 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
     } else {
         // fused solver: cc.cpp:354-357 are ONE product Rt[i,a,b,j] = sum_me t_imae W_mbej evaluated at four
         // index relabelings, likewise :360-363 with (t_ie t_ma) <mb||je>; two GEMMs + one P(ij)P(ab) combine
-        DBuf rt(ctx, (size_t) o2v2);
-        const TView Rt(rt.p, {O, V, V, O});
-        contract(ctx, 1.0, td, "imae", Wmbej, "mbej", 0.0, Rt, "iabj");
-        contract(ctx, 1.0, vtt, "iema", ovov, "mbje", 1.0, Rt, "iabj");
+        // Both left factors are laid out as [i,a | m,e] first, so each product is one plain (ov)^3 GEMM.
+        DBuf rt(ctx, (size_t) o2v2), lf(ctx, (size_t) o2v2);
+        const TView Rt(rt.p, {O, V, V, O}), Lf(lf.p, {O, V, O, V});
+        {
+            const long long ext[4] = {O, V, O, V}, istr[4] = {O * V * V, V, V * V, 1};// t[i,m,a,e] read as [i,a,m,e]
+            permute_axpby(ctx, lf.p, Td, 4, ext, istr, 1.0, 0.0);
+        }
+        contract(ctx, 1.0, Lf, "iame", Wmbej, "mbej", 0.0, Rt, "iabj");
+        ring_tt(ctx, Ts, o, v, lf.p);                                       // t_ie t_ma as [i,a,m,e]
+        contract(ctx, 1.0, Lf, "iame", ovov, "mbje", 1.0, Rt, "iabj");
         ring_combine(ctx, rt, o, v, r);
     }
+    if (fused) {
+        contract(ctx, 1.0, ts, "ie", vvvo, "abej", 0.0, U, "ijab");         // :366
+        antisym_add(ctx, U.p, nullptr, o, v, 0, r);                         // - (i<->j) (:367)
+        contract(ctx, -1.0, ts, "ma", ovoo, "mbij", 0.0, U, "ijab");        // :370
+        antisym_add(ctx, U.p, nullptr, o, v, 1, r);                         // - (a<->b) (:371)
+    } else {
     contract(ctx, 1.0, ts, "ie", vvvo, "abej", 1.0, R, "ijab");         // :366
     contract(ctx, -1.0, ts, "je", vvvo, "abei", 1.0, R, "ijab");        // :367
     contract(ctx, -1.0, ts, "ma", ovoo, "mbij", 1.0, R, "ijab");        // :370
     contract(ctx, 1.0, ts, "mb", ovoo, "maij", 1.0, R, "ijab");         // :371
+    }
     if (D_ijab) divide_elementwise(ctx, r, D_ijab, o2v2, T2_new);        // :374-383
     else divide_D_ijab(ctx, r, foo, fvv, o, v, T2_new);
 }
@@ -320,6 +354,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         }
     } cache_guard(ctx, perm_cache);
     if (getenv("QCP2_CCSD_NO_PERM_CACHE")) ctx.perm_cache = nullptr;
+    unsigned long long *chk_dev = static_cast<unsigned long long *>(ctx.alloc_bytes(32));
     fill_zero(ctx, T1, O * V);                                                             // :417-419
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
     cudaEvent_t ev0, ev1;
@@ -330,8 +365,22 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     int it = 0;
     for (; it < maxiter; ++it) {
         ccsd_energy(ctx, T1, T2, I.p[I_OOVV], fov, o, v, e_dev);                           // :432
+        // the packed ladder needs antisymmetric doubles (tau = T2 + an antisymmetric product of singles); the check
+        // rides on the iteration's one host synchronisation instead of stalling the stream inside make_T2
+        unsigned long long chk[4] = {0, 0, 0, 0};
+        if (pack.vvvvP) {
+            QCP2_CUDA(cudaMemsetAsync(chk_dev, 0, 32, ctx.stream));
+            antisymmetry_defect_async(ctx, T2, O, O, V, V, 0, chk_dev);
+            antisymmetry_defect_async(ctx, T2, O, O, V, V, 1, chk_dev + 2);
+            QCP2_CUDA(cudaMemcpyAsync(chk, chk_dev, 32, cudaMemcpyDeviceToHost, ctx.stream));
+        }
         QCP2_CUDA(cudaMemcpyAsync(&e, e_dev.p, 8, cudaMemcpyDeviceToHost, ctx.stream));
         ctx.sync();
+        if (pack.vvvvP) {
+            double dm[4];
+            memcpy(dm, chk, 32);
+            pack.tau_antisymmetric = (dm[0] <= 1e-10 * dm[1] && dm[2] <= 1e-10 * dm[3]) ? 1 : 0;
+        }
         const double de = e - e_last;
         e_last = e;
         if (e_hist_host) e_hist_host[it] = e;
@@ -350,6 +399,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
     if (pairs_dev) cudaFree(pairs_dev);
+    ctx.free(chk_dev);
     *e_host = e;
     if (iters_host) *iters_host = it;
 }

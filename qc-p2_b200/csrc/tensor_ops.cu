@@ -576,6 +576,52 @@ void ring_combine(Ctx &ctx, const double *Rt, int o, int v, double *r) {
     ctx.launched("ring_combine");
 }
 
+// r[i,j,a,b] = (init ? init : r)[i,j,a,b] + U[i,j,a,b] - U[j,i,a,b] (pair 0) / - U[i,j,b,a] (pair 1):
+// the P(ij) / P(ab) partner of a product is the same product with two labels exchanged
+__global__ void antisym_add_kernel(const double *__restrict__ U, const double *__restrict__ init, int o, int v, int pair,
+                                   double *__restrict__ r) {
+    const long long n = (long long) o * o * v * v, vv = (long long) v * v;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        const int b = (int) (q % v);
+        q /= v;
+        const int a = (int) (q % v);
+        q /= v;
+        const int j = (int) (q % o);
+        const int i = (int) (q / o);
+        const long long other = pair == 0 ? ((long long) j * o + i) * vv + (long long) a * v + b
+                                          : ((long long) i * o + j) * vv + (long long) b * v + a;
+        r[lin] = (init ? init[lin] : r[lin]) + U[lin] - U[other];
+    }
+}
+void antisym_add(Ctx &ctx, const double *U, const double *init, int o, int v, int pair, double *r) {
+    const long long n = (long long) o * o * v * v;
+    if (n == 0) return;
+    antisym_add_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(U, init, o, v, pair, r);
+    ctx.launched("antisym_add");
+}
+
+// out[i,a,m,e] = Ts[i,e] Ts[m,a]: multiply_Ts (cc.cpp:158-172) in the (free | contracted) order of cc.cpp:360
+__global__ void ring_tt_kernel(const double *__restrict__ ts, int o, int v, double *__restrict__ out) {
+    const long long n = (long long) o * v * o * v;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        const int e = (int) (q % v);
+        q /= v;
+        const int m = (int) (q % o);
+        q /= o;
+        const int a = (int) (q % v);
+        const int i = (int) (q / v);
+        out[lin] = ts[i * v + e] * ts[m * v + a];
+    }
+}
+void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out) {
+    const long long n = (long long) o * v * o * v;
+    if (n == 0) return;
+    ring_tt_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(Ts, o, v, out);
+    ctx.launched("ring_tt");
+}
+
 __global__ void pack_pairs_kernel(const double *__restrict__ src, int d01, int d23, const int *__restrict__ pairs01,
                                   double *__restrict__ dst) {
     const int a = pairs01[2 * blockIdx.x], b = pairs01[2 * blockIdx.x + 1];
@@ -664,6 +710,19 @@ __global__ void antisym_kernel(const double *__restrict__ x, long long d0, long 
         atomicMax(res + 1, (unsigned long long) __double_as_longlong(mx));
     }
 }
+// asynchronous form: accumulates (max) into res[0..1] on the device; the caller zeroes res and reads it
+// back with whatever synchronisation point it already has
+void antisymmetry_defect_async(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,
+                               unsigned long long *res) {
+    if (pair == 0) QCP2_REQUIRE(d0 == d1, "antisymmetry check: extents differ");
+    else QCP2_REQUIRE(d2 == d3, "antisymmetry check: extents differ");
+    const long long n = d0 * d1 * d2 * d3;
+    if (n > 0) {
+        antisym_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(x, d0, d1, d2, d3, pair, res);
+        ctx.launched("antisym");
+    }
+}
+
 void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,
                          double *defect, double *maxabs) {
     if (pair == 0) QCP2_REQUIRE(d0 == d1, "antisymmetry check: extents differ");

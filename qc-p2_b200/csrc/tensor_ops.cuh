@@ -37,6 +37,10 @@ void ccsd_energy(Ctx &ctx, const double *Ts, const double *Td, const double *oov
 void extract_diag(Ctx &ctx, const double *F, int n, double *d);
 // r[i,j,a,b] += Rt[i,a,b,j] - Rt[j,a,b,i] - Rt[i,b,a,j] + Rt[j,b,a,i]   (P(ij)P(ab) of one ring product)
 void ring_combine(Ctx &ctx, const double *Rt, int o, int v, double *r);
+// r = (init ? init : r) + U - U[j,i,a,b] (pair 0) or - U[i,j,b,a] (pair 1); all [o,o,v,v]
+void antisym_add(Ctx &ctx, const double *U, const double *init, int o, int v, int pair, double *r);
+// out[i,a,m,e] = Ts[i,e] Ts[m,a]
+void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out);
 
 // dst[row][q(e<f)] = src[a_row][b_row][e][f] for the rows (a<b) listed in pairs01 (2 ints per row); src is [d01,d01,d23,d23]
 void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst);
@@ -46,5 +50,7 @@ void unpack_add_pairs(Ctx &ctx, const double *LP, int o, int v, double *r);
 // max |x + P x| over an index-pair transposition, relative to max|x| -> host values
 void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,
                          double *defect, double *maxabs);
+void antisymmetry_defect_async(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,
+                               unsigned long long *res);
 
 }// namespace qcp2

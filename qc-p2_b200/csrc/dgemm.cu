@@ -44,14 +44,14 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     }
     // tile choice: estimated SM clocks = waves x per-CTA clocks (DMMA-bound: 64 FMA/clk/SM) plus, for
     // split-K, the bandwidth-bound reduction pass (~3400 B/clk chip-wide) and its launch
-    const TileChoice cand[4] = {{64, 64, 0.70}, {112, 128, 0.88}, {128, 128, 0.90}, {80, 256, 0.90}};
+    const TileChoice cand[5] = {{64, 64, 0.70}, {112, 128, 0.88}, {128, 128, 0.90}, {80, 256, 0.90}, {48, 128, 0.80}};
     const int nkb = (g.K + GEMM_BK - 1) / GEMM_BK;
     double best = 1e300;
     int best_t = 0, best_split = 1;
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < 5; ++t) {
         if (t == 3 && !(a_kc && b_nc)) continue;// the 80x256 tile is instantiated for [M][K] x [K][N] only
         const long long tiles = (long long) ((g.M + cand[t].bm - 1) / cand[t].bm) * ((g.N + cand[t].bn - 1) / cand[t].bn) * g.batch;
-        const int cta_per_sm = cand[t].bm == 64 ? 2 : 1;
+        const int cta_per_sm = cand[t].bm <= 64 ? 2 : 1;
         const long long slots = (long long) ctx.sm_count * cta_per_sm;
         // split-K candidates: powers of two and the factors that fill exactly one wave (skinny products with a
         // huge contracted dimension -- M, N <= a tile, K = o v^2 -- are bound by how many CTAs stream K)
@@ -63,7 +63,10 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
             if (split > 1 && (nkb / split < 4 || tiles * split > 4 * slots || t == 3)) continue;
             const long long ctas = tiles * split;
             const double waves = (double) ((ctas + slots - 1) / slots);
-            const double conc = (double) std::min<long long>(cta_per_sm, (ctas + ctx.sm_count - 1) / ctx.sm_count);
+            // co-resident CTAs share the tensor pipe -- unless the tile is mostly padding (M or N <= 16), where the
+            // product is bound by the latency of streaming K and a second CTA per SM simply doubles the bytes in flight
+            const bool skinny = g.M <= 16 || g.N <= 16;
+            const double conc = skinny ? 1.0 : (double) std::min<long long>(cta_per_sm, (ctas + ctx.sm_count - 1) / ctx.sm_count);
             const double kb = (double) ((nkb + split - 1) / split) + 6.0;// + prologue/epilogue overhead in k-block units
             double cost = waves * conc * cand[t].bm * cand[t].bn * kb / (4.0 * cand[t].eff);
             if (split > 1) cost += 8.0 * g.M * g.N * g.batch * (split + 1) / 3400.0 + 3000.0;
@@ -83,7 +86,8 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
         run.alpha = 1.0, run.beta = 0.0;
         run.k_splits = best_split, run.kb_per_split = (nkb + best_split - 1) / best_split;
     }
-    if (best_t == 3) launch_dgemm_t(ctx, run, vec, false);
+    if (best_t == 4) launch_dgemm_48(ctx, run, a_kc, b_nc, vec);
+    else if (best_t == 3) launch_dgemm_t(ctx, run, vec, false);
     else if (best_t == 2) launch_dgemm_128(ctx, run, a_kc, b_nc, vec);
     else if (best_t == 1) launch_dgemm_112(ctx, run, a_kc, b_nc, vec);
     else launch_dgemm_64(ctx, run, a_kc, b_nc, vec);

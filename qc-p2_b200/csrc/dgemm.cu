@@ -1,4 +1,7 @@
 // dgemm.cu -- alignment analysis, tile selection and split-K for the DMMA GEMM.
+#include <cstdio>
+#include <cstdlib>
+
 #include "dgemm.cuh"
 
 namespace qcp2 {
@@ -44,14 +47,16 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     }
     // tile choice: estimated SM clocks = waves x per-CTA clocks (DMMA-bound: 64 FMA/clk/SM) plus, for
     // split-K, the bandwidth-bound reduction pass (~3400 B/clk chip-wide) and its launch
-    const TileChoice cand[5] = {{64, 64, 0.70}, {112, 128, 0.88}, {128, 128, 0.90}, {80, 256, 0.90}, {48, 128, 0.80}};
+    const TileChoice cand[7] = {{64, 64, 0.70}, {112, 128, 0.88}, {128, 128, 0.90}, {80, 256, 0.90}, {48, 128, 0.80},
+                                {16, 256, 0.60}, {256, 16, 0.60}};
     const int nkb = (g.K + GEMM_BK - 1) / GEMM_BK;
     double best = 1e300;
     int best_t = 0, best_split = 1;
-    for (int t = 0; t < 5; ++t) {
-        if (t == 3 && !(a_kc && b_nc)) continue;// the 80x256 tile is instantiated for [M][K] x [K][N] only
+    for (int t = 0; t < 7; ++t) {
+        if (t == 3 && !(a_kc && b_nc)) continue;
+        if ((t == 5 && g.M > 16) || (t == 6 && g.N > 16)) continue;// skinny tiles// the 80x256 tile is instantiated for [M][K] x [K][N] only
         const long long tiles = (long long) ((g.M + cand[t].bm - 1) / cand[t].bm) * ((g.N + cand[t].bn - 1) / cand[t].bn) * g.batch;
-        const int cta_per_sm = cand[t].bm <= 64 ? 2 : 1;
+        const int cta_per_sm = (cand[t].bm <= 64 || t == 6) ? 2 : 1;
         const long long slots = (long long) ctx.sm_count * cta_per_sm;
         // split-K candidates: powers of two and the factors that fill exactly one wave (skinny products with a
         // huge contracted dimension -- M, N <= a tile, K = o v^2 -- are bound by how many CTAs stream K)
@@ -86,7 +91,13 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
         run.alpha = 1.0, run.beta = 0.0;
         run.k_splits = best_split, run.kb_per_split = (nkb + best_split - 1) / best_split;
     }
-    if (best_t == 4) launch_dgemm_48(ctx, run, a_kc, b_nc, vec);
+    static const bool trace = getenv("QCP2_GEMM_TRACE") != nullptr;
+    if (trace)
+        fprintf(stderr, "[qcp2 gemm] M %d N %d K %d batch %d  a_kc %d b_nc %d -> tile %dx%d split %d\n", g.M, g.N, g.K, g.batch, (int) a_kc,
+                (int) b_nc, cand[best_t].bm, cand[best_t].bn, best_split);
+    if (best_t == 6) launch_dgemm_16n(ctx, run, a_kc, b_nc, vec);
+    else if (best_t == 5) launch_dgemm_16m(ctx, run, a_kc, b_nc, vec);
+    else if (best_t == 4) launch_dgemm_48(ctx, run, a_kc, b_nc, vec);
     else if (best_t == 3) launch_dgemm_t(ctx, run, vec, false);
     else if (best_t == 2) launch_dgemm_128(ctx, run, a_kc, b_nc, vec);
     else if (best_t == 1) launch_dgemm_112(ctx, run, a_kc, b_nc, vec);

@@ -255,7 +255,10 @@ void launch_dgemm_inst(Ctx &ctx, const GemmArgs &g) {
 }
 
 using Tile64 = GemmTile<64, 64, 32, 32, 3>;
-using Tile48 = GemmTile<48, 128, 48, 16, 3>;// M = o(o-1)/2 = 45 rows of the packed particle-particle ladder
+using Tile48 = GemmTile<48, 128, 48, 16, 3>;
+// skinny products (one free dimension = o <= 16, the other o v^2): HBM-bound streaming of the big operand
+using Tile16M = GemmTile<16, 256, 16, 32, 3>;
+using Tile16N = GemmTile<256, 16, 32, 16, 3>;// M = o(o-1)/2 = 45 rows of the packed particle-particle ladder
 using Tile128 = GemmTile<128, 128, 64, 32, 3>;
 using Tile112 = GemmTile<112, 128, 56, 32, 3>;// skinny M = o^2 = 100 (particle-particle ladder)
 using TileT = GemmTile<80, 256, 40, 64, 3>;
@@ -265,6 +268,8 @@ using TileT16 = GemmTile<80, 256, 40, 32, 3>;// 16-warp experiment
 // the instantiations compile in parallel)
 void launch_dgemm_64(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
 void launch_dgemm_48(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
+void launch_dgemm_16m(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
+void launch_dgemm_16n(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
 void launch_dgemm_128(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
 void launch_dgemm_112(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int vec);
 void launch_dgemm_t(Ctx &ctx, const GemmArgs &g, int vec, bool seg);

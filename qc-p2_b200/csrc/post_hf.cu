@@ -245,15 +245,16 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
         }
         if (packed) {
             // sum over e<f only (x2 cancels the 1/2), rows i<j, columns a<b: 1/8 of the flops of the dense product
-            DBuf tauP(ctx, (size_t) pack->npo * pack->npv), lp(ctx, (size_t) pack->npo * pack->npv);
-            pack_pairs(ctx, tau, o, v, pack->pairs_o, pack->npo, tauP);
+            const long long ld = pack->ld;// even: 16-byte aligned rows
+            DBuf tauP(ctx, (size_t) (pack->npo * ld)), lp(ctx, (size_t) (pack->npo * ld));
+            pack_pairs(ctx, tau, o, v, pack->pairs_o, pack->npo, tauP, ld);
             GemmArgs g;
             g.M = pack->npo, g.N = pack->npv, g.K = pack->npv;
-            g.A = tauP, g.lda = pack->npv;         // [M][K]
-            g.B = pack->vvvvP, g.ldb = pack->npv;  // [N][K]
-            g.C = lp, g.ldc = pack->npv;
+            g.A = tauP, g.lda = ld;         // [M][K]
+            g.B = pack->vvvvP, g.ldb = ld;  // [N][K]
+            g.C = lp, g.ldc = ld;
             gemm(ctx, g, true, false);
-            unpack_add_pairs(ctx, lp, o, v, r);
+            unpack_add_pairs(ctx, lp, ld, o, v, r);
         } else {
             contract(ctx, 0.5, vtau, "ijef", vvvv, "abef", 1.0, R, "ijab");// 1/2 tau <ab||ef>         (cc.cpp:240 in :348)
         }
@@ -335,8 +336,9 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
             QCP2_CUDA(cudaMemcpy(pairs_dev, po.data(), po.size() * sizeof(int), cudaMemcpyHostToDevice));
             QCP2_CUDA(cudaMemcpy(pairs_dev + po.size(), pv.data(), pv.size() * sizeof(int), cudaMemcpyHostToDevice));
             pack.npo = (int) (po.size() / 2), pack.npv = (int) (pv.size() / 2);
-            vvvvP = DBuf(ctx, (size_t) pack.npv * pack.npv);
-            pack_pairs(ctx, I.p[I_VVVV], v, v, pairs_dev + po.size(), pack.npv, vvvvP);
+            pack.ld = ((long long) pack.npv + 1) & ~1LL;
+            vvvvP = DBuf(ctx, (size_t) (pack.npv * pack.ld));
+            pack_pairs(ctx, I.p[I_VVVV], v, v, pairs_dev + po.size(), pack.npv, vvvvP, pack.ld);
             pack.vvvvP = vvvvP.p, pack.pairs_o = pairs_dev;
         }
     }

@@ -14,6 +14,7 @@ struct LadderPack {
     const double *vvvvP = nullptr;// [v(v-1)/2][v(v-1)/2]
     const int *pairs_o = nullptr; // device, 2 ints per i<j pair
     int npo = 0, npv = 0;
+    long long ld = 0;            // row stride of the packed operands (npv rounded up to even)
     // >= 0: the caller already knows whether the doubles amplitudes (hence tau) are antisymmetric in (i,j) and
     // (a,b) (ccsd_dev reads the check back together with the iteration's energy); < 0: check tau here
     int tau_antisymmetric = -1;

@@ -623,24 +623,24 @@ void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out) {
 }
 
 __global__ void pack_pairs_kernel(const double *__restrict__ src, int d01, int d23, const int *__restrict__ pairs01,
-                                  double *__restrict__ dst) {
+                                  double *__restrict__ dst, long long ld) {
     const int a = pairs01[2 * blockIdx.x], b = pairs01[2 * blockIdx.x + 1];
-    const size_t n23 = (size_t) d23 * (d23 - 1) / 2;
     const double *s = src + ((size_t) a * d01 + b) * d23 * d23;
-    double *d = dst + (size_t) blockIdx.x * n23;
-    for (int e = 0; e + 1 < d23; ++e) {
+    double *d = dst + (size_t) blockIdx.x * (size_t) ld;
+    for (int e = blockIdx.y; e + 1 < d23; e += gridDim.y) {// blockIdx.y strides the rows so few pairs still fill the GPU
         const size_t q0 = (size_t) e * d23 - (size_t) e * (e + 1) / 2 - (e + 1);// q(e,f) = q0 + f
         for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) d[q0 + f] = s[(size_t) e * d23 + f];
     }
 }
-void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst) {
+void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld) {
     if (n01 <= 0 || d23 < 2) return;
-    pack_pairs_kernel<<<(unsigned) n01, kBlock, 0, ctx.stream>>>(src, d01, d23, pairs01, dst);
+    const unsigned ny = n01 >= 4 * ctx.sm_count ? 1u : (unsigned) std::min(d23 - 1, (4 * ctx.sm_count + n01 - 1) / n01);
+    pack_pairs_kernel<<<dim3((unsigned) n01, ny), kBlock, 0, ctx.stream>>>(src, d01, d23, pairs01, dst, ld);
     ctx.launched("pack_pairs");
 }
 
-__global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, int o, int v, double *__restrict__ r) {
-    const long long n = (long long) o * o * v * v, npv = (long long) v * (v - 1) / 2;
+__global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, long long npv, int o, int v, double *__restrict__ r) {
+    const long long n = (long long) o * o * v * v;// npv = row stride of LP (>= v(v-1)/2)
     GRID_STRIDE(lin, n) {
         long long q = lin;
         int b = (int) (q % v);
@@ -664,10 +664,10 @@ __global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, int o, in
         r[lin] += sign * LP[pij * npv + pab];
     }
 }
-void unpack_add_pairs(Ctx &ctx, const double *LP, int o, int v, double *r) {
+void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, double *r) {
     const long long n = (long long) o * o * v * v;
     if (n == 0 || o < 2 || v < 2) return;
-    unpack_add_pairs_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(LP, o, v, r);
+    unpack_add_pairs_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(LP, ld, o, v, r);
     ctx.launched("unpack_add_pairs");
 }
 

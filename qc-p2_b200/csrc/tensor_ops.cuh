@@ -43,9 +43,10 @@ void antisym_add(Ctx &ctx, const double *U, const double *init, int o, int v, in
 void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out);
 
 // dst[row][q(e<f)] = src[a_row][b_row][e][f] for the rows (a<b) listed in pairs01 (2 ints per row); src is [d01,d01,d23,d23]
-void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst);
+// dst rows are `ld` doubles apart (ld >= d23 (d23-1)/2; an even ld keeps the rows 16-byte aligned for the GEMM's vector copies)
+void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld);
 // r[i,j,a,b] += sgn(ij) sgn(ab) LP[p(i,j)][p(a,b)]  (zero on the diagonals); LP is [o(o-1)/2][v(v-1)/2]
-void unpack_add_pairs(Ctx &ctx, const double *LP, int o, int v, double *r);
+void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, double *r);
 
 // max |x + P x| over an index-pair transposition, relative to max|x| -> host values
 void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,

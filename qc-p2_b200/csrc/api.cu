@@ -79,21 +79,6 @@ int guarded(qcp2_ctx *ctx, F &&f) {
 
 long long ipow4(long long n) { return n * n * n * n; }
 
-// QCP2_TRACE=1: wall-clock phase marks (each mark synchronises the stream) on stderr
-struct Trace {
-    Ctx &c;
-    const char *what;
-    bool on;
-    std::chrono::steady_clock::time_point t0;
-    Trace(Ctx &ctx, const char *w) : c(ctx), what(w), on(getenv("QCP2_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
-    void mark(const char *phase) {
-        if (!on) return;
-        c.sync();
-        const auto t1 = std::chrono::steady_clock::now();
-        fprintf(stderr, "[qcp2 trace] %s: %-44s %9.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
-        t0 = t1;
-    }
-};
 
 }// namespace
 
@@ -249,6 +234,7 @@ int qcp2_mp2(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const doubl
         QCP2_REQUIRE(ao_ints && Ca && eps_a && energy && n >= 1, "MP2: null argument");
         if (uhf) QCP2_REQUIRE(Cb && eps_b, "MP2: UHF needs Cb and eps_b");
         const long long n4 = ipow4(n);
+        Trace tr(c, "qcp2_post_hf");
         In ao(c, ao_ints, n4), ca(c, Ca, (long long) n * n), ea(c, eps_a, n);
         In cb = uhf ? In(c, Cb, (long long) n * n) : In();
         In eb = uhf ? In(c, eps_b, n) : In();
@@ -779,6 +765,7 @@ int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const d
         if (stages >= 3) QCP2_REQUIRE(e_t, "post_hf: (T) output missing");
         const long long n4 = ipow4(n), O = o, V = v, o2v2 = O * O * V * V;
         const int n2 = 2 * n;
+        Trace tr(c, "qcp2_post_hf");
         In ao(c, ao_ints, n4), ca(c, Ca, (long long) n * n), ea(c, eps_a, n);
         In cb = uhf ? In(c, Cb, (long long) n * n) : In();
         In eb = uhf ? In(c, eps_b, n) : In();
@@ -788,7 +775,9 @@ int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const d
         DBuf blocks[I_COUNT];
         {
             DBuf so(c, (size_t) (16 * n4));
+            tr.mark("stage AO integrals + allocate <pq||rs>");
             mp2_dev(c, ao, ca, uhf ? cb.p : ca.p, pea, peb, n, o, v, uhf != 0, so, t2_mp2, e_mp2);// mp2.cpp:45-86
+            tr.mark("AO->MO, to_so, MP2");
             if (stages >= 2)
                 for (int k = 0; k < I_COUNT; ++k) {// get_integrals, cc.cpp:8-23
                     blocks[k] = DBuf(c, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
@@ -796,6 +785,7 @@ int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const d
                     I.p[k] = blocks[k].p;
                 }
         }// the (2n)^4 tensor is released here
+        tr.mark("slice the 11 blocks");
         if (stages < 2) return;
         DBuf foo(c, (size_t) (O * O)), fvv(c, (size_t) (V * V)), F(c, (size_t) ((long long) n2 * n2));
         make_so_moes(c, pea, peb, n, F);// same diagonal as make_fock(eps_a, eps_b, 0, no+nv), cc.cpp:25-34
@@ -812,6 +802,7 @@ int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const d
         if (!t2p) t2own = DBuf(c, (size_t) std::max<long long>(o2v2, 1)), t2p = t2own.p;
         ccsd_dev(c, I, foo, nullptr, fvv, t2_mp2, o, v, maxiter, conv, t1p, t2p, e_ccsd, iters, e_hist);// cc.cpp:409-451
         t1.finish(), t2.finish();
+        tr.mark("CCSD iterations");
         if (stages >= 3) {// cc.cpp:454-560
             DBuf eo(c, (size_t) std::max(o, 1)), ev(c, (size_t) std::max(v, 1));
             extract_diag(c, foo, o, eo);
@@ -819,6 +810,7 @@ int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const d
             const int mode = t_select_mode(c, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], o, v);
             std::unique_ptr<TPlan> plan(t_plan_create(c, t1p, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], eo, ev, o, v, mode));
             t_plan_run(*plan, 0, 1, -1, nullptr, e_t);
+            tr.mark("(T)");
         }
         c.sync();
     });

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -76,6 +78,22 @@ struct Ctx {
         ++launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) throw Error(std::string("kernel launch failed (") + what + "): " + cudaGetErrorString(e));
+    }
+};
+
+// QCP2_TRACE=1: wall-clock phase marks (each mark synchronises the stream) on stderr
+struct Trace {
+    Ctx &c;
+    const char *what;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace(Ctx &ctx, const char *w) : c(ctx), what(w), on(getenv("QCP2_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *phase) {
+        if (!on) return;
+        c.sync();
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[qcp2 trace] %s: %-44s %9.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
     }
 };
 

@@ -321,11 +321,14 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     // the as-written UHF integrals lose the ket antisymmetry, SURVEY.md Q5, and take the dense product)
     LadderPack pack;
     DBuf vvvvP;
+    Trace tr(ctx, "ccsd_dev");
     int *pairs_dev = nullptr;
     if (o >= 2 && v >= 2 && !getenv("QCP2_CCSD_DENSE_LADDER")) {
         double d0, d1, m0, m1;
         antisymmetry_defect(ctx, I.p[I_VVVV], V, V, V, V, 0, &d0, &m0);
+        tr.mark("antisymmetry of <vv||vv> in (a,b)");
         antisymmetry_defect(ctx, I.p[I_VVVV], V, V, V, V, 1, &d1, &m1);
+        tr.mark("antisymmetry of <vv||vv> in (e,f)");
         if (d0 <= 1e-10 * m0 && d1 <= 1e-10 * m1) {
             std::vector<int> po, pv;
             for (int i = 0; i < o; ++i)
@@ -340,6 +343,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
             vvvvP = DBuf(ctx, (size_t) (pack.npv * pack.ld));
             pack_pairs(ctx, I.p[I_VVVV], v, v, pairs_dev + po.size(), pack.npv, vvvvP, pack.ld);
             pack.vvvvP = vvvvP.p, pack.pairs_o = pairs_dev;
+            tr.mark("pack <vv||vv> to a<b, e<f");
         }
     }
     // the integral blocks are constant for the whole loop: their operand re-layouts are made once
@@ -395,6 +399,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     }
     QCP2_CUDA(cudaEventRecord(ev1, ctx.stream));
     QCP2_CUDA(cudaEventSynchronize(ev1));
+    tr.mark("iteration loop");
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     ctx.ccsd_loop_seconds = ms * 1e-3;

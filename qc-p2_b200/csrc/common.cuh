@@ -39,6 +39,7 @@ struct PermCache {
     };
     std::vector<const double *> constants;
     std::vector<Entry> entries;
+    bool frozen = false;// no new entries (while the iteration is being captured into a CUDA graph)
     bool is_constant(const double *p) const {
         for (const double *c : constants)
             if (c == p) return true;

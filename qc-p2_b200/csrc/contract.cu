@@ -116,11 +116,12 @@ const double *operand_relayout(Ctx &ctx, DBuf &tmp, const double *src, long long
         for (const PermCache::Entry &e : pc->entries)
             if (e.src == src && e.sig == sig) return e.buf;
     }
+    const bool store = cacheable && !pc->frozen;
     double *dst;
-    if (cacheable) dst = ctx.alloc((size_t) (n * nb));
+    if (store) dst = ctx.alloc((size_t) (n * nb));
     else tmp = DBuf(ctx, (size_t) (n * nb)), dst = tmp.p;
     for (int z = 0; z < nb; ++z) relayout(ctx, dst + z * n, src + z * stride, from, efrom, to, 1.0, 0.0);
-    if (cacheable) pc->entries.push_back(PermCache::Entry{src, sig, dst});
+    if (store) pc->entries.push_back(PermCache::Entry{src, sig, dst});
     return dst;
 }
 

@@ -369,6 +369,20 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     QCP2_CUDA(cudaEventRecord(ev0, ctx.stream));
     double e_last = 0.0, e = 0.0;
     int it = 0;
+    // One iteration (cc.cpp:442-446) is a fixed sequence of ~90 launches on fixed buffers: from the second iteration
+    // on it is replayed as a CUDA graph (stream capture, incl. the stream-ordered workspace allocations), which
+    // removes the launch gaps that dominate small molecules.  QCP2_CCSD_NO_GRAPH=1 keeps the eager path.
+    auto body = [&]() {
+        update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
+        make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);                 // :445
+        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1, &pack);          // :446: new T1, old T2, old X
+        QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    };
+    bool use_graph = getenv("QCP2_CCSD_NO_GRAPH") == nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_flag = -2;
+    long long graph_launches = 0;
     for (; it < maxiter; ++it) {
         ccsd_energy(ctx, T1, T2, I.p[I_OOVV], fov, o, v, e_dev);                           // :432
         // the packed ladder needs antisymmetric doubles (tau = T2 + an antisymmetric product of singles); the check
@@ -391,11 +405,44 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         e_last = e;
         if (e_hist_host) e_hist_host[it] = e;
         if (std::fabs(de) < conv) break;                                                   // :438 (fabs)
-        update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
-        make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);                          // :445
-        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1, &pack);                              // :446: new T1, old T2, old X
-        QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
-        QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        if (!use_graph || it == 0) {// the first iteration runs eagerly: it fills the re-layout cache and configures the kernels
+            body();
+            continue;
+        }
+        if (!graph_exec || graph_flag != pack.tau_antisymmetric) {
+            if (graph_exec) cudaGraphExecDestroy(graph_exec), graph_exec = nullptr;
+            const long long l0 = ctx.launches;
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                perm_cache.frozen = true;
+                try {
+                    body();
+                } catch (const std::exception &) {
+                    ok = false;
+                }
+                perm_cache.frozen = false;
+                if (cudaStreamEndCapture(ctx.stream, &graph) != cudaSuccess || !graph) ok = false;
+            }
+            if (ok && cudaGraphInstantiate(&graph_exec, graph, 0) != cudaSuccess) ok = false, graph_exec = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();// a failed capture leaves a sticky-free error behind; the eager path below is always valid
+            if (!ok) {
+                ctx.launches = l0;
+                use_graph = false;
+                body();
+                continue;
+            }
+            graph_launches = ctx.launches - l0;
+            ctx.launches = l0;
+            graph_flag = pack.tau_antisymmetric;
+        }
+        QCP2_CUDA(cudaGraphLaunch(graph_exec, ctx.stream));
+        ctx.launches += graph_launches;
+    }
+    if (graph_exec) {
+        cudaStreamSynchronize(ctx.stream);
+        cudaGraphExecDestroy(graph_exec);
     }
     QCP2_CUDA(cudaEventRecord(ev1, ctx.stream));
     QCP2_CUDA(cudaEventSynchronize(ev1));

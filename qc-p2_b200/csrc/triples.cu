@@ -240,10 +240,11 @@ struct EnergySymArgs {
     long long np;
 };
 
-__global__ void __launch_bounds__(kEBlock) t_energy_sym_kernel(EnergySymArgs p) {
+template<int EB, int MINB>
+__global__ void __launch_bounds__(EB, MINB) t_energy_sym_kernel(EnergySymArgs p) {
     __shared__ double Mt[32][33];
     __shared__ double qb[3][32], tbs[3][32], evb[32];
-    __shared__ double ws[kEBlock / 32];
+    __shared__ double ws[EB / 32];
     const int t = blockIdx.y;
     const int a = p.items[3 * blockIdx.x], bt = p.items[3 * blockIdx.x + 1], ct = p.items[3 * blockIdx.x + 2];
     const int s0 = a + 1, v = p.v;
@@ -257,11 +258,11 @@ __global__ void __launch_bounds__(kEBlock) t_energy_sym_kernel(EnergySymArgs p) 
     const int b0 = s0 + bt * 32, c0 = s0 + ct * 32, c = c0 + tx;
     const bool c_ok = c < v;
 #pragma unroll
-    for (int rr = ty; rr < 32; rr += kEBlock / 32) {// M_a[c rows][b cols], transposed on read-out
+    for (int rr = ty; rr < 32; rr += EB / 32) {// M_a[c rows][b cols], transposed on read-out
         const int row = c0 + rr, col = b0 + tx;
         Mt[rr][tx] = (row < v && col < v) ? X[row * inp + pa + col] : 0.0;
     }
-    if (threadIdx.x < 96) {
+    if (threadIdx.x < 96) {// (EB >= 128)
         const int w = threadIdx.x >> 5;
         const double *Owp = w == 0 ? O0 : (w == 1 ? O1 : O2);
         const long long ow = w == 0 ? i : (w == 1 ? j : k);
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kEBlock) t_energy_sym_kernel(EnergySymArgs p) 
     __syncthreads();
     double sum = 0.0;
 #pragma unroll
-    for (int r = ty; r < 32; r += kEBlock / 32) {
+    for (int r = ty; r < 32; r += EB / 32) {
         const int b = b0 + r;
         if (b < c && c_ok) {
             const int pbc = b * v - ((b * (b + 1)) >> 1) + (c - b - 1);
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kEBlock) t_energy_sym_kernel(EnergySymArgs p) 
     if (threadIdx.x == 0) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < kEBlock / 32; ++w) s += ws[w];
+        for (int w = 0; w < EB / 32; ++w) s += ws[w];
         p.partial[(long long) t * gridDim.x + blockIdx.x] = s;
     }
 }
@@ -746,7 +747,10 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
             es.items = P.items_dev;
             if (P.sym_items > 0) {
                 dim3 grid((unsigned) P.sym_items, (unsigned) cnt, 1);
-                t_energy_sym_kernel<<<grid, kEBlock, 0, P.aux>>>(es);
+                // <= 56 registers (9 resident blocks); measured under ncu on 5 triples of o=40/v=400: 85 registers
+                // (no occupancy hint) 638 us, 56 -> 417 us, 40 -> 449 us, 32 (spills) -> 417 us: past ~50 % occupancy the
+                // sweep is bound by the latency of its dependent loads, not by residency
+                t_energy_sym_kernel<128, 9><<<grid, 128, 0, P.aux>>>(es);
             } else {
                 QCP2_CUDA(cudaMemsetAsync(P.partial[s].p, 0, (size_t) cnt * sizeof(double), P.aux));
             }

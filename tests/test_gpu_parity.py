@@ -26,7 +26,10 @@ def close(a, b, rel=1e-12):
 # ---------------------------------------------------------------------------- GEMM / contract
 @pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 16), (65, 63, 17), (100, 26244 // 4, 33), (38, 1444, 144),
                                    (400, 1000, 88), (130, 257, 1320), (1, 300, 70), (300, 1, 70), (81, 39, 1521),
-                                   (100, 2000, 5000), (10, 162, 40000), (162, 162, 16200), (3, 5, 70000)])  # split-K / 112-row tile shapes
+                                   (100, 2000, 5000), (10, 162, 40000), (162, 162, 16200), (3, 5, 70000),  # split-K / 112-row tile shapes
+                                   (10, 5001, 162), (5001, 10, 162), (16, 700, 35), (701, 16, 33),   # skinny 16x256 / 256x16 tiles
+                                   (45, 1001, 3001), (48, 129, 2000), (33, 257, 513),                 # 48x128 tile, odd strides
+                                   (10, 10, 50001), (1, 3000, 1621), (3000, 1, 1621), (9, 39, 13689)])  # one-wave split-K factors
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_dgemm_matches_numpy(ctx, M, N, K, tA, tB):
     rng = np.random.default_rng(M * 7 + N * 3 + K)

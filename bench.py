@@ -456,6 +456,9 @@ def main():
     if rank == 0 and not args.no_ccsd:
         try:
             ccsd = ccsd_seconds_per_iter(torch, qcp2_b200, ctx, cpu_sample=(world == 1 and not args.no_cpu_baseline))
+            ccsd["parallelism"] = ("single GPU" if world == 1 else
+                                   "replica on rank 0 (the iteration does not shard at these sizes: after the packed ladder its largest "
+                                   "term is 0.6 ms, below an all-gather of T2 + launch; DESIGN.md section 6)")
         except Exception as ex:  # never lose the headline line to the secondary metric
             ccsd = {"error": str(ex)[:200]}
 

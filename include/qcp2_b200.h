@@ -162,6 +162,22 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
                      const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode, int root,
                      double *e_triples, double *energy);
 
+/* Fused MP2 -> CCSD -> (T) across the communicator (collective; same n, o, v, uhf, stages, maxiter, conv, root
+ * on every rank).  Rank `root` supplies the boundary inputs of qcp2_post_hf (host or device pointers per its pointer
+ * mode), the others may pass NULL.  The inputs are broadcast; AO->MO, <pq||rs>, MP2 and the slicing run replicated
+ * (milliseconds); in every CCSD iteration the large products (particle-particle ladder over occupied pairs i<j, ring
+ * and W_mbej products, tau.<am||ef>) are split by rows over the ranks and re-assembled with one ncclBroadcast per
+ * rank (an all-gather with unequal counts), everything else is replicated, so all ranks hold identical amplitudes; the
+ * (T) triples are dealt round-robin and combined with one ncclAllReduce.  Every rank returns the same energies.
+ * QCP2_CCSD_NO_SHARD=1 keeps the iteration replicated.  qcp2_sharded_gemms: products split so far on this context. */
+int qcp2_post_hf_mgpu(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
+                      const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, int root,
+                      double *e_mp2, double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2);
+long long qcp2_sharded_gemms(const qcp2_ctx *ctx);
+/* enable != 0: qcp2_ccsd becomes collective over the context's communicator (every rank must pass IDENTICAL inputs)
+ * and splits the large products of each iteration as qcp2_post_hf_mgpu does */
+int qcp2_set_ccsd_sharding(qcp2_ctx *ctx, int enable);
+
 /* Resident (T) plan: packs/repacks the inputs once (device pointers required) so repeated
  * range evaluations (bench steps, multi-rank shards) reuse them. */
 typedef struct qcp2_t_plan qcp2_t_plan;

@@ -21,6 +21,7 @@ using namespace qcp2;
 struct qcp2_ctx {
     Ctx c;
     Comm *comm = nullptr;// NCCL communicator (qcp2_comm_init); null = single GPU
+    bool ccsd_sharding = false;// qcp2_set_ccsd_sharding: qcp2_ccsd is collective and splits its large products
 };
 struct qcp2_t_plan {
     qcp2_ctx *owner = nullptr;
@@ -445,6 +446,11 @@ int qcp2_ccsd(qcp2_ctx *ctx, const double *so_ints, int n2, const double *const 
             I = given->dev;
         }
         Out t1(c, T1, O * V), t2(c, T2, O * O * V * V);
+        struct ShardGuard {
+            Ctx &c;
+            ShardGuard(Ctx &ctx_, Comm *s) : c(ctx_) { c.shard = s; }
+            ~ShardGuard() { c.shard = nullptr; }
+        } guard(c, (ctx->ccsd_sharding && ctx->comm && ctx->comm->nranks > 1) ? ctx->comm : nullptr);
         ccsd_dev(c, I, foo, f_ov ? fov.p : nullptr, fvv, guess, o, v, maxiter, conv, t1, t2, energy, iters, e_hist);
         t1.finish(), t2.finish();
         if (sliced_out)
@@ -754,66 +760,136 @@ int qcp2_t_plan_destroy(qcp2_t_plan *plan) {
     return 0;
 }
 
+namespace {
+// Body of qcp2_post_hf / qcp2_post_hf_mgpu.  cm == nullptr: single GPU.  With a communicator the call is
+// collective: the root's boundary inputs are broadcast, MP2 / slicing run replicated (milliseconds), the large
+// products of every CCSD iteration are row-sharded (dgemm.cu) and the (T) triples dealt round-robin.
+void post_hf_impl(Ctx &c, Comm *cm, int root, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
+                  const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, double *e_mp2,
+                  double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2) {
+    const bool multi = cm && cm->nranks > 1;
+    const bool is_root = !multi || cm->rank == root;
+    if (is_root) QCP2_REQUIRE(ao_ints && Ca && eps_a, "post_hf: null argument");
+    QCP2_REQUIRE(e_mp2 && n >= 1, "post_hf: null argument");
+    QCP2_REQUIRE(stages >= 1 && stages <= 3, "post_hf: stages must be 1, 2 or 3");
+    if (uhf && is_root) QCP2_REQUIRE(Cb && eps_b, "post_hf: UHF needs Cb and eps_b");
+    if (stages >= 2) QCP2_REQUIRE(e_ccsd && maxiter >= 0, "post_hf: CCSD outputs missing");
+    if (stages >= 3) QCP2_REQUIRE(e_t, "post_hf: (T) output missing");
+    const long long n4 = ipow4(n), O = o, V = v, o2v2 = O * O * V * V;
+    const int n2 = 2 * n;
+    Trace tr(c, multi ? "qcp2_post_hf_mgpu" : "qcp2_post_hf");
+    // boundary inputs on the device: staged / used in place on the root, received into scratch elsewhere
+    DBuf scratch[5];
+    auto place = [&](const double *src, long long count, int slot) -> In {
+        if (is_root) return In(c, src, count);
+        scratch[slot] = DBuf(c, (size_t) std::max<long long>(count, 1));
+        In in;
+        in.p = scratch[slot].p;
+        return in;
+    };
+    In ao = place(ao_ints, n4, 0), ca = place(Ca, (long long) n * n, 1), ea = place(eps_a, n, 2);
+    In cb = uhf ? place(Cb, (long long) n * n, 3) : In();
+    In eb = uhf ? place(eps_b, n, 4) : In();
+    if (multi) {
+        comm_broadcast(c, *cm, const_cast<double *>(ao.p), n4, root);
+        comm_broadcast(c, *cm, const_cast<double *>(ca.p), (long long) n * n, root);
+        comm_broadcast(c, *cm, const_cast<double *>(ea.p), n, root);
+        if (uhf) comm_broadcast(c, *cm, const_cast<double *>(cb.p), (long long) n * n, root), comm_broadcast(c, *cm, const_cast<double *>(eb.p), n, root);
+    }
+    const double *pea = ea.p, *peb = uhf ? eb.p : ea.p;
+    DBuf t2_mp2(c, (size_t) std::max<long long>(o2v2, 1));
+    IntsDev I;
+    DBuf blocks[I_COUNT];
+    {
+        DBuf so(c, (size_t) (16 * n4));
+        tr.mark("stage AO integrals + allocate <pq||rs>");
+        mp2_dev(c, ao, ca, uhf ? cb.p : ca.p, pea, peb, n, o, v, uhf != 0, so, t2_mp2, e_mp2);// mp2.cpp:45-86
+        tr.mark("AO->MO, to_so, MP2");
+        if (stages >= 2)
+            for (int k = 0; k < I_COUNT; ++k) {// get_integrals, cc.cpp:8-23
+                blocks[k] = DBuf(c, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
+                slice_block(c, so, n2, o, v, kIntNames[k], blocks[k]);
+                I.p[k] = blocks[k].p;
+            }
+    }// the (2n)^4 tensor is released here
+    tr.mark("slice the 11 blocks");
+    if (stages < 2) return;
+    DBuf foo(c, (size_t) (O * O)), fvv(c, (size_t) (V * V)), F(c, (size_t) ((long long) n2 * n2));
+    make_so_moes(c, pea, peb, n, F);// same diagonal as make_fock(eps_a, eps_b, 0, no+nv), cc.cpp:25-34
+    {
+        const long long oo[2] = {O, O}, so2[2] = {n2, 1};
+        permute_axpby(c, foo, F.p, 2, oo, so2, 1.0, 0.0);
+        const long long vv[2] = {V, V};
+        permute_axpby(c, fvv, F.p + O * n2 + O, 2, vv, so2, 1.0, 0.0);
+    }
+    Out t1(c, T1, O * V), t2(c, T2, o2v2);
+    DBuf t1own, t2own;
+    double *t1p = t1.p, *t2p = t2.p;
+    if (!t1p) t1own = DBuf(c, (size_t) std::max<long long>(O * V, 1)), t1p = t1own.p;
+    if (!t2p) t2own = DBuf(c, (size_t) std::max<long long>(o2v2, 1)), t2p = t2own.p;
+    {
+        struct ShardGuard {// row-sharded products for the duration of the iteration loop only
+            Ctx &c;
+            ShardGuard(Ctx &ctx_, Comm *s) : c(ctx_) { c.shard = s; }
+            ~ShardGuard() { c.shard = nullptr; }
+        } guard(c, multi && !getenv("QCP2_CCSD_NO_SHARD") ? cm : nullptr);
+        ccsd_dev(c, I, foo, nullptr, fvv, t2_mp2, o, v, maxiter, conv, t1p, t2p, e_ccsd, iters, e_hist);// cc.cpp:409-451
+    }
+    t1.finish(), t2.finish();
+    tr.mark("CCSD iterations");
+    if (stages >= 3) {// cc.cpp:454-560
+        DBuf eo(c, (size_t) std::max(o, 1)), ev(c, (size_t) std::max(v, 1));
+        extract_diag(c, foo, o, eo);
+        extract_diag(c, fvv, v, ev);
+        const int mode = t_select_mode(c, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], o, v);
+        std::unique_ptr<TPlan> plan(t_plan_create(c, t1p, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], eo, ev, o, v, mode));
+        if (!multi) {
+            t_plan_run(*plan, 0, 1, -1, nullptr, e_t);
+        } else {// the amplitudes and blocks are already replicated: round-robin triples, one all-reduce, fixed-order sum
+            const long long nt = plan->ntriples;
+            DBuf et(c, (size_t) std::max<long long>(nt, 1));
+            fill_zero(c, et, nt);
+            double partial = 0.0;
+            t_plan_run(*plan, cm->rank, cm->nranks, -1, et.p, &partial);
+            comm_allreduce_sum(c, *cm, et.p, nt);
+            std::vector<double> h((size_t) std::max<long long>(nt, 1), 0.0);
+            if (nt > 0) QCP2_CUDA(cudaMemcpyAsync(h.data(), et.p, (size_t) nt * 8, cudaMemcpyDeviceToHost, c.stream));
+            c.sync();
+            double total = 0.0;
+            for (long long t = 0; t < nt; ++t) total += h[(size_t) t];
+            *e_t = total;
+        }
+        tr.mark("(T)");
+    }
+    c.sync();
+}
+}// namespace
+
 int qcp2_post_hf(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
                  const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, double *e_mp2,
                  double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2) {
     return guarded(ctx, [&](Ctx &c) {
-        QCP2_REQUIRE(ao_ints && Ca && eps_a && e_mp2 && n >= 1, "post_hf: null argument");
-        QCP2_REQUIRE(stages >= 1 && stages <= 3, "post_hf: stages must be 1, 2 or 3");
-        if (uhf) QCP2_REQUIRE(Cb && eps_b, "post_hf: UHF needs Cb and eps_b");
-        if (stages >= 2) QCP2_REQUIRE(e_ccsd && maxiter >= 0, "post_hf: CCSD outputs missing");
-        if (stages >= 3) QCP2_REQUIRE(e_t, "post_hf: (T) output missing");
-        const long long n4 = ipow4(n), O = o, V = v, o2v2 = O * O * V * V;
-        const int n2 = 2 * n;
-        Trace tr(c, "qcp2_post_hf");
-        In ao(c, ao_ints, n4), ca(c, Ca, (long long) n * n), ea(c, eps_a, n);
-        In cb = uhf ? In(c, Cb, (long long) n * n) : In();
-        In eb = uhf ? In(c, eps_b, n) : In();
-        const double *pea = ea.p, *peb = uhf ? eb.p : ea.p;
-        DBuf t2_mp2(c, (size_t) std::max<long long>(o2v2, 1));
-        IntsDev I;
-        DBuf blocks[I_COUNT];
-        {
-            DBuf so(c, (size_t) (16 * n4));
-            tr.mark("stage AO integrals + allocate <pq||rs>");
-            mp2_dev(c, ao, ca, uhf ? cb.p : ca.p, pea, peb, n, o, v, uhf != 0, so, t2_mp2, e_mp2);// mp2.cpp:45-86
-            tr.mark("AO->MO, to_so, MP2");
-            if (stages >= 2)
-                for (int k = 0; k < I_COUNT; ++k) {// get_integrals, cc.cpp:8-23
-                    blocks[k] = DBuf(c, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
-                    slice_block(c, so, n2, o, v, kIntNames[k], blocks[k]);
-                    I.p[k] = blocks[k].p;
-                }
-        }// the (2n)^4 tensor is released here
-        tr.mark("slice the 11 blocks");
-        if (stages < 2) return;
-        DBuf foo(c, (size_t) (O * O)), fvv(c, (size_t) (V * V)), F(c, (size_t) ((long long) n2 * n2));
-        make_so_moes(c, pea, peb, n, F);// same diagonal as make_fock(eps_a, eps_b, 0, no+nv), cc.cpp:25-34
-        {
-            const long long oo[2] = {O, O}, so2[2] = {n2, 1};
-            permute_axpby(c, foo, F.p, 2, oo, so2, 1.0, 0.0);
-            const long long vv[2] = {V, V};
-            permute_axpby(c, fvv, F.p + O * n2 + O, 2, vv, so2, 1.0, 0.0);
-        }
-        Out t1(c, T1, O * V), t2(c, T2, o2v2);
-        DBuf t1own, t2own;
-        double *t1p = t1.p, *t2p = t2.p;
-        if (!t1p) t1own = DBuf(c, (size_t) std::max<long long>(O * V, 1)), t1p = t1own.p;
-        if (!t2p) t2own = DBuf(c, (size_t) std::max<long long>(o2v2, 1)), t2p = t2own.p;
-        ccsd_dev(c, I, foo, nullptr, fvv, t2_mp2, o, v, maxiter, conv, t1p, t2p, e_ccsd, iters, e_hist);// cc.cpp:409-451
-        t1.finish(), t2.finish();
-        tr.mark("CCSD iterations");
-        if (stages >= 3) {// cc.cpp:454-560
-            DBuf eo(c, (size_t) std::max(o, 1)), ev(c, (size_t) std::max(v, 1));
-            extract_diag(c, foo, o, eo);
-            extract_diag(c, fvv, v, ev);
-            const int mode = t_select_mode(c, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], o, v);
-            std::unique_ptr<TPlan> plan(t_plan_create(c, t1p, t2p, I.p[I_OOVV], I.p[I_VOVV], I.p[I_OVOO], eo, ev, o, v, mode));
-            t_plan_run(*plan, 0, 1, -1, nullptr, e_t);
-            tr.mark("(T)");
-        }
-        c.sync();
+        post_hf_impl(c, nullptr, 0, ao_ints, Ca, Cb, eps_a, eps_b, n, o, v, uhf, stages, maxiter, conv, e_mp2, e_ccsd, e_t, iters, e_hist,
+                     T1, T2);
     });
+}
+
+int qcp2_post_hf_mgpu(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
+                      const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, int root,
+                      double *e_mp2, double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(!ctx->comm || (root >= 0 && root < ctx->comm->nranks), "post_hf_mgpu: root out of range");
+        post_hf_impl(c, ctx->comm, root, ao_ints, Ca, Cb, eps_a, eps_b, n, o, v, uhf, stages, maxiter, conv, e_mp2, e_ccsd, e_t, iters,
+                     e_hist, T1, T2);
+    });
+}
+
+long long qcp2_sharded_gemms(const qcp2_ctx *ctx) { return ctx ? ctx->c.sharded_gemms : 0; }
+
+int qcp2_set_ccsd_sharding(qcp2_ctx *ctx, int enable) {
+    if (!ctx) return 2;
+    ctx->ccsd_sharding = enable != 0;
+    return 0;
 }
 
 // ---- building blocks ----------------------------------------------------------------

@@ -27,6 +27,8 @@ struct NcclApi {
     int (*Broadcast)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 
@@ -48,9 +50,12 @@ NcclApi &api() {
         a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
         a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
         a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
+        a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
+        a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
     });
-    if (!a.handle || !a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Broadcast || !a.AllReduce || !a.AllGather)
+    if (!a.handle || !a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Broadcast || !a.AllReduce || !a.AllGather || !a.GroupStart ||
+        !a.GroupEnd)
         throw Error("NCCL is not available (dlopen of libnccl.so.2 failed or symbols are missing)");
     return a;
 }
@@ -104,6 +109,9 @@ void comm_allreduce_sum(Ctx &ctx, Comm &comm, double *buf, long long n) {
     if (n <= 0 || comm.nranks == 1) return;
     check(api().AllReduce(buf, buf, (size_t) n, kNcclFloat64, kNcclSum, comm.nccl, ctx.stream), "ncclAllReduce");
 }
+
+void comm_group_start() { check(api().GroupStart(), "ncclGroupStart"); }
+void comm_group_end() { check(api().GroupEnd(), "ncclGroupEnd"); }
 
 void comm_allgather(Ctx &ctx, Comm &comm, const double *send, double *recv, long long n_per_rank) {
     if (n_per_rank <= 0) return;

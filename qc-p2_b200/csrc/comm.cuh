@@ -18,6 +18,9 @@ void comm_destroy(Comm *comm);
 void comm_broadcast(Ctx &ctx, Comm &comm, double *buf, long long n, int root);
 void comm_broadcast_bytes(Ctx &ctx, Comm &comm, void *buf, long long nbytes, int root);
 void comm_allreduce_sum(Ctx &ctx, Comm &comm, double *buf, long long n);
+// several collectives issued as one NCCL group (e.g. one broadcast per rank with unequal counts)
+void comm_group_start();
+void comm_group_end();
 void comm_allgather(Ctx &ctx, Comm &comm, const double *send, double *recv, long long n_per_rank);
 
 }// namespace qcp2

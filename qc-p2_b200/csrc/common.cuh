@@ -59,6 +59,11 @@ struct Ctx {
     std::string last_error;
     double ccsd_loop_seconds = 0.0;
     PermCache *perm_cache = nullptr;
+    // row-sharded GEMMs (dgemm.cu): while set, every product above shard_min_flops whose result is a dense row-major
+    // matrix is split by rows over the communicator's ranks and re-assembled with one broadcast per rank
+    struct Comm *shard = nullptr;
+    double shard_min_flops = 2.0e9;
+    long long sharded_gemms = 0;
 
     double *alloc(size_t n_doubles) {
         void *p = nullptr;

@@ -2,7 +2,9 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "comm.cuh"
 #include "dgemm.cuh"
+#include "tensor_ops.cuh"
 
 namespace qcp2 {
 
@@ -38,6 +40,69 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     else {
         v2 = v2 && g.seg_aligned;
         for (int s = 0; s < g.nseg; ++s) v2 = v2 && (g.seg_ldb[s] % 2 == 0);
+    }
+    // multi-GPU: the product is split over the ranks along its LONGER free dimension, so that the larger operand
+    // is streamed only once in total.  Rows: rank r computes rows [r R, (r+1) R) of C into its slab of a W x R row
+    // workspace, ONE in-place ncclAllGather assembles the product on every rank, the first M rows are copied to C.
+    // Columns (N > M, beta = 0): the same on the transposed problem C^T = B^T A^T, followed by a transposing copy.
+    // Every rank takes the same decision (same shapes, same threshold), so the collectives match up.
+    if (ctx.shard && ctx.shard->nranks > 1 && g.seg == nullptr && g.batch == 1 && g.k_splits == 1 &&
+        (g.ldc == g.N || g.c_owns_rows) && 2.0 * g.M * g.N * g.K >= ctx.shard_min_flops) {
+        Comm *cm = ctx.shard;
+        const int W = cm->nranks;
+        const bool by_cols = g.N > g.M && g.beta == 0.0 && g.N >= 2 * W;
+        if (by_cols || g.M >= 2 * W) {
+            const long long ext = by_cols ? g.N : g.M;           // the sharded extent
+            const long long width = by_cols ? g.M : g.ldc;       // row length of the gathered workspace
+            const long long R = (ext + W - 1) / W;
+            const long long x0 = std::min<long long>(ext, cm->rank * R), x1 = std::min<long long>(ext, x0 + R);
+            DBuf gathered(ctx, (size_t) (W * R * width));
+            double *slab = gathered.p + cm->rank * R * width;
+            ctx.shard = nullptr;// the slab itself is an ordinary product
+            try {
+                if (x1 > x0) {
+                    GemmArgs part = g;
+                    part.c_owns_rows = false;
+                    if (!by_cols) {
+                        part.M = (int) (x1 - x0);
+                        part.A = g.A + (a_kc ? x0 * g.lda : x0);
+                        part.C = slab;
+                        if (g.beta != 0.0) {// beta term: this rank's rows of the (replicated) C
+                            part.Cin = (g.Cin ? g.Cin + x0 * g.ldcin : g.C + x0 * g.ldc);
+                            part.ldcin = g.Cin ? g.ldcin : g.ldc;
+                        }
+                        gemm(ctx, part, a_kc, b_nc);
+                    } else {// slab of C^T: [x1-x0][M] = (B[:, x0:x1])^T . A^T
+                        part.M = (int) (x1 - x0), part.N = g.M;
+                        part.A = g.B + (b_nc ? x0 : x0 * g.ldb), part.lda = g.ldb;
+                        part.B = g.A, part.ldb = g.lda;
+                        part.C = slab, part.ldc = g.M;
+                        part.Cin = nullptr;
+                        gemm(ctx, part, /*a_kc=*/!b_nc, /*b_nc=*/!a_kc);
+                    }
+                }
+                comm_allgather(ctx, *cm, slab, gathered.p, R * width);
+                if (!by_cols) {
+                    QCP2_CUDA(cudaMemcpyAsync(g.C, gathered.p, (size_t) ((long long) g.M * g.ldc) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+                } else {// C[m][n] = gathered[n][m]
+                    const long long oext[2] = {g.M, g.N}, istr[2] = {1, g.M};
+                    if (g.ldc == g.N) {
+                        permute_axpby(ctx, g.C, gathered.p, 2, oext, istr, 1.0, 0.0);
+                    } else {// padded rows (c_owns_rows): transpose row by row block
+                        DBuf dense(ctx, (size_t) ((long long) g.M * g.N));
+                        permute_axpby(ctx, dense.p, gathered.p, 2, oext, istr, 1.0, 0.0);
+                        QCP2_CUDA(cudaMemcpy2DAsync(g.C, (size_t) g.ldc * 8, dense.p, (size_t) g.N * 8, (size_t) g.N * 8, (size_t) g.M,
+                                                    cudaMemcpyDeviceToDevice, ctx.stream));
+                    }
+                }
+            } catch (...) {
+                ctx.shard = cm;
+                throw;
+            }
+            ctx.shard = cm;
+            ++ctx.sharded_gemms;
+            return;
+        }
     }
     const int vec = v2 ? 2 : 1;
     if (g.seg != nullptr) {

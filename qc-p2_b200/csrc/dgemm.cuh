@@ -43,6 +43,9 @@ struct GemmArgs {
     // split-K: grid.y = k_splits, split s handles k-blocks [s*kb_per_split, ...) and writes its raw
     // partial product to C + (batch*k_splits + s) * strideC (the launcher points C at a workspace)
     int k_splits = 1, kb_per_split = 0;
+    // the caller owns every element of the M x ldc region behind C (padding columns included), so whole rows may
+    // be exchanged between ranks by the row-sharded path
+    bool c_owns_rows = false;
     // SEG mode
     const SegDesc *seg = nullptr;
     int nseg = 0;

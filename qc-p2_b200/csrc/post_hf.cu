@@ -252,7 +252,7 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
             g.M = pack->npo, g.N = pack->npv, g.K = pack->npv;
             g.A = tauP, g.lda = ld;         // [M][K]
             g.B = pack->vvvvP, g.ldb = ld;  // [N][K]
-            g.C = lp, g.ldc = ld;
+            g.C = lp, g.ldc = ld, g.c_owns_rows = true;
             gemm(ctx, g, true, false);
             unpack_add_pairs(ctx, lp, ld, o, v, r);
         } else {
@@ -379,7 +379,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     };
-    bool use_graph = getenv("QCP2_CCSD_NO_GRAPH") == nullptr;
+    bool use_graph = getenv("QCP2_CCSD_NO_GRAPH") == nullptr && ctx.shard == nullptr;// (NCCL calls stay outside graphs)
     cudaGraphExec_t graph_exec = nullptr;
     int graph_flag = -2;
     long long graph_launches = 0;

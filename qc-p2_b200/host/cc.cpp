@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <iostream>
 
 #include "gpu.h"
@@ -171,6 +172,7 @@ real_t CCSD_T(const cc_results &cc, const moes &m) {// cc.cpp:454-560
         // `P2 --gpus N`: the workers join through their pipes; tensors are replicated by ncclBroadcast from this
         // rank, triples dealt round-robin, one ncclAllReduce -- same energy, bit for bit
         MgpuCommand cmd;
+        std::memset(&cmd, 0, sizeof(cmd));
         cmd.cmd = 1, cmd.o = o, cmd.v = v;
         if (qcp2_comm_get_unique_id(cmd.id, QCP2_COMM_ID_BYTES) != 0) throw std::runtime_error("qcp2_b200: NCCL is not available");
         mgpu_send(cmd);

@@ -24,8 +24,10 @@ inline MgpuState &mgpu() {
     return s;
 }
 struct MgpuCommand {
-    int cmd;// 0 = exit, 1 = join qcp2_ccsd_t_mgpu
+    int cmd;// 0 = exit, 1 = join qcp2_ccsd_t_mgpu, 2 = join qcp2_post_hf_mgpu
     int o, v;
+    int n, uhf, stages, maxiter;// cmd 2
+    double conv;
     char id[QCP2_COMM_ID_BYTES];
 };
 
@@ -64,8 +66,15 @@ inline void gpu_release() {
         try {
             double e = 0.0;
             gpu_check(qcp2_comm_init(gpu(), m.id, mgpu().world, mgpu().rank));
-            gpu_check(qcp2_ccsd_t_mgpu(gpu(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m.o, m.v, QCP2_T_AUTO, 0,
-                                       nullptr, &e));
+            if (m.cmd == 1) {
+                gpu_check(qcp2_ccsd_t_mgpu(gpu(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, m.o, m.v, QCP2_T_AUTO, 0,
+                                           nullptr, &e));
+            } else {
+                double e2 = 0.0, ecc = 0.0;
+                int iters = 0;
+                gpu_check(qcp2_post_hf_mgpu(gpu(), nullptr, nullptr, nullptr, nullptr, nullptr, m.n, m.o, m.v, m.uhf, m.stages, m.maxiter,
+                                            m.conv, 0, &e2, &ecc, &e, &iters, nullptr, nullptr, nullptr));
+            }
             gpu_check(qcp2_comm_destroy(gpu()));
         } catch (const std::exception &ex) {
             fprintf(stderr, "P2 worker %d: %s\n", mgpu().rank, ex.what());

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iomanip>
 #include <iostream>
 
@@ -29,8 +30,8 @@ int main(int argc, char *argv[]) {
         else if (argc >= 3 && std::string(argv[1]) == "--gpus") gpus = std::atoi(argv[2]), argc -= 2, argv += 2;
         else break;
     }
-    if (argc < 2 || gpus < 1 || (fused && gpus > 1)) {
-        std::cerr << "usage: P2 [--fused | --gpus N] <input.json>" << endl;
+    if (argc < 2 || gpus < 1) {
+        std::cerr << "usage: P2 [--fused] [--gpus N] <input.json>" << endl;
         return 2;
     }
     try {
@@ -69,6 +70,20 @@ int main(int argc, char *argv[]) {
                 const int stages = (t == "MP2" || t == "mp2") ? 1 : ((t == "CCSD" || t == "ccsd") ? 2 : 3);
                 int iters = 0;
                 std::vector<double> hist((size_t) std::max(config.maxiter, 1), 0.0);
+                if (mgpu().world > 1) {// every rank joins the collective pipeline: sharded CCSD products, round-robin (T)
+                    MgpuCommand cmd;
+                    std::memset(&cmd, 0, sizeof(cmd));
+                    cmd.cmd = 2, cmd.o = hf.no, cmd.v = hf.nv, cmd.n = hf.nao, cmd.uhf = is_uhf ? 1 : 0, cmd.stages = stages;
+                    cmd.maxiter = config.maxiter, cmd.conv = config.cc_conv;
+                    if (qcp2_comm_get_unique_id(cmd.id, QCP2_COMM_ID_BYTES) != 0) throw std::runtime_error("qcp2_b200: NCCL is not available");
+                    mgpu_send(cmd);
+                    gpu_check(qcp2_comm_init(gpu(), cmd.id, mgpu().world, 0));
+                    gpu_check(qcp2_post_hf_mgpu(gpu(), ao.data(), is_rhf ? hf.C.data() : hf.Ca.data(), is_rhf ? nullptr : hf.Cb.data(),
+                                                is_rhf ? hf.moes.data() : hf.moes_a.data(), is_rhf ? nullptr : hf.moes_b.data(), hf.nao,
+                                                hf.no, hf.nv, is_uhf ? 1 : 0, stages, config.maxiter, config.cc_conv, 0, &e_mp2, &e_cc, &e_t,
+                                                &iters, hist.data(), nullptr, nullptr));
+                    gpu_check(qcp2_comm_destroy(gpu()));
+                } else
                 gpu_check(qcp2_post_hf(gpu(), ao.data(), is_rhf ? hf.C.data() : hf.Ca.data(), is_rhf ? nullptr : hf.Cb.data(),
                                        is_rhf ? hf.moes.data() : hf.moes_a.data(), is_rhf ? nullptr : hf.moes_b.data(), hf.nao, hf.no,
                                        hf.nv, is_uhf ? 1 : 0, stages, config.maxiter, config.cc_conv, &e_mp2, &e_cc, &e_t, &iters,

@@ -45,6 +45,7 @@ def load_library():
         lib.qcp2_kernel_launches.restype = C.c_longlong
         lib.qcp2_ccsd_t_count.restype = C.c_longlong
         lib.qcp2_ccsd_last_loop_seconds.restype = C.c_double
+        lib.qcp2_sharded_gemms.restype = C.c_longlong
         _lib = lib
     return _lib
 
@@ -344,6 +345,25 @@ class Context:
         self.check(self.lib.qcp2_ccsd_t_mgpu(self.h, *[_p(a) for a in args], int(o), int(v), int(mode), int(root),
                                              _p(et), C.byref(E)))
         return (E.value, et) if want_triples else E.value
+
+    def post_hf_mgpu(self, ao_ints, Ca, Cb, eps_a, eps_b, n, no, nv, uhf=False, stages=3, maxiter=200, cc_conv=1e-12, root=0):
+        """qcp2_post_hf_mgpu (collective): the root rank passes the boundary inputs, the others None."""
+        conv = (lambda a: a) if (ao_ints is not None and not isinstance(ao_ints, np.ndarray)) else _arr
+        ao, ca, ea = (conv(x) if x is not None else None for x in (ao_ints, Ca, eps_a))
+        cb, eb = ((conv(Cb), conv(eps_b)) if (uhf and Cb is not None) else (None, None))
+        e2, ecc, et, iters = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        hist = np.zeros(max(maxiter, 1))
+        self.check(self.lib.qcp2_post_hf_mgpu(self.h, _p(ao), _p(ca), _p(cb), _p(ea), _p(eb), int(n), int(no), int(nv), int(bool(uhf)),
+                                              int(stages), int(maxiter), C.c_double(cc_conv), int(root), C.byref(e2), C.byref(ecc),
+                                              C.byref(et), C.byref(iters), _p(hist), None, None))
+        return dict(e_mp2=e2.value, e_ccsd=ecc.value, e_t=et.value, iters=iters.value, e_hist=hist[:min(iters.value + 1, maxiter)])
+
+    def set_ccsd_sharding(self, enable):
+        self.check(self.lib.qcp2_set_ccsd_sharding(self.h, int(bool(enable))))
+
+    @property
+    def sharded_gemms(self):
+        return int(self.lib.qcp2_sharded_gemms(self.h))
 
     def t_count(self, o, mode):
         return int(self.lib.qcp2_ccsd_t_count(o, mode))

@@ -41,6 +41,8 @@ enum { QCP2_HOST = 0, QCP2_DEVICE = 1 };
 enum { QCP2_T_AUTO = 0, QCP2_T_LITERAL = 1, QCP2_T_SYMMETRIC = 2 };
 
 /* ---- context ------------------------------------------------------------------------ */
+/* number of CUDA devices visible to the process (0 without a driver / device) */
+int qcp2_device_count(void);
 int qcp2_create(int device, qcp2_ctx **ctx);
 int qcp2_destroy(qcp2_ctx *ctx);
 int qcp2_set_pointer_mode(qcp2_ctx *ctx, int mode);

@@ -87,6 +87,15 @@ extern "C" {
 
 const char *qcp2_version(void) { return "qcp2_b200 0.1 (sm_100a, DMMA.8x8x4)"; }
 
+int qcp2_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return ndev;
+}
+
 int qcp2_create(int device, qcp2_ctx **out) {
     if (!out) return 2;
     *out = nullptr;

@@ -537,6 +537,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     const long long xbytes = std::max<long long>(V * P->ncols * 8, 8);
     tb = std::min(tb, std::max<long long>(1, (4LL << 30) / xbytes));
     tb = std::max<long long>(1, std::min<long long>(tb, std::min<long long>(4096, std::max<long long>(P->ntriples, 1))));
+    if (const char *env = getenv("QCP2_T_BATCH")) tb = std::max<long long>(1, std::min<long long>(atoll(env), std::max<long long>(P->ntriples, 1)));// experiments
     P->tb = (int) tb;
     {
         if (sym) {// work items (a, bt <= ct) of the tiled energy sweep

@@ -7,6 +7,7 @@
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -88,6 +89,15 @@ inline void gpu_release() {
 // fork world-1 workers; returns in rank 0 only
 inline void mgpu_spawn(int world) {
     if (world <= 1) return;
+    {// count the GPUs in a throw-away child, so that this process still forks without a CUDA context
+        const pid_t probe = fork();
+        if (probe < 0) throw std::runtime_error("P2 --gpus: fork() failed");
+        if (probe == 0) _exit(std::min(qcp2_device_count(), 255));
+        int st = 0;
+        waitpid(probe, &st, 0);
+        const int ndev = WIFEXITED(st) ? WEXITSTATUS(st) : 0;
+        if (ndev < world) throw std::runtime_error("P2 --gpus " + std::to_string(world) + ": only " + std::to_string(ndev) + " GPU(s) visible");
+    }
     MgpuState &s = mgpu();
     s.world = world;
     for (int r = 1; r < world; ++r) {

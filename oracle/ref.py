@@ -78,6 +78,15 @@ def inter_shapes(o, v):
     return [(v, v), (o, o), (o, v), (o, o, o, o), (o, v, v, o), (v, v, v, v)]
 
 
+def shim_contract(alpha, A, ia, B, ib, beta, Cin, ic):
+    """The shim's btas::contract (oracle/ref_shim/include/btas/btas.h) on label strings -- for testing the shim."""
+    A, B, Cout = _c(A), _c(B), _c(Cin).copy()
+    ext = lambda t: (C.c_long * t.ndim)(*t.shape)
+    _chk(lib().ref_shim_contract(C.c_double(alpha), _p(A), ext(A), ia.encode(), _p(B), ext(B), ib.encode(),
+                                 C.c_double(beta), _p(Cout), ext(Cout), ic.encode()))
+    return Cout
+
+
 def transform_ao_mo(ao, C1, C2):
     """integrals.cpp:95-134"""
     ao, C1, C2 = _c(ao), _c(C1), _c(C2)

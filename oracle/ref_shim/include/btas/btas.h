@@ -117,13 +117,9 @@ inline void gather(const Tensor<double> &T, const std::vector<int> &lab, const s
 }
 }// namespace detail
 
-template<typename S, typename UA, typename UB, typename UC>
-void contract(const S &alpha, const Tensor<double> &A, std::initializer_list<UA> aA, const Tensor<double> &B,
-              std::initializer_list<UB> aB, const S &beta, Tensor<double> &C, std::initializer_list<UC> aC) {
-    std::vector<int> la, lb, lc;
-    for (auto x : aA) la.push_back(static_cast<int>(x));
-    for (auto x : aB) lb.push_back(static_cast<int>(x));
-    for (auto x : aC) lc.push_back(static_cast<int>(x));
+// label-vector form (what the initializer-list front end below forwards to; also exported for the shim's own test)
+inline void contract_labels(double alpha, const Tensor<double> &A, const std::vector<int> &la, const Tensor<double> &B,
+                            const std::vector<int> &lb, double beta, Tensor<double> &C, const std::vector<int> &lc) {
     if (lc.size() != C.rank()) throw std::invalid_argument("btas shim: contract: C rank/labels mismatch");
     if (A.empty() || B.empty()) {// Q4: an empty operand is zeros
         if (static_cast<double>(beta) != 1.0)
@@ -198,6 +194,16 @@ void contract(const S &alpha, const Tensor<double> &A, std::initializer_list<UA>
             double &dst = c[roff[static_cast<size_t>(i)] + coff[static_cast<size_t>(j)]];
             dst = be * dst + al * Cp[static_cast<size_t>(i * N + j)];
         }
+}
+
+template<typename S, typename UA, typename UB, typename UC>
+void contract(const S &alpha, const Tensor<double> &A, std::initializer_list<UA> aA, const Tensor<double> &B,
+              std::initializer_list<UB> aB, const S &beta, Tensor<double> &C, std::initializer_list<UC> aC) {
+    std::vector<int> la, lb, lc;
+    for (auto x : aA) la.push_back(static_cast<int>(x));
+    for (auto x : aB) lb.push_back(static_cast<int>(x));
+    for (auto x : aC) lc.push_back(static_cast<int>(x));
+    contract_labels(static_cast<double>(alpha), A, la, B, lb, static_cast<double>(beta), C, lc);
 }
 
 }// namespace btas

@@ -131,6 +131,34 @@ int count_cc_iterations(const std::string &log) {// lines " %02d %20.12f %20.12f
 
 extern "C" {
 
+// the shim's btas::contract itself (label strings, one character per index), so that the restated third-party
+// semantics can be held against an independent einsum (tests/test_ref_pins_oracle.py)
+int ref_shim_contract(double alpha, const double *A, const long *extA, const char *ia, const double *B, const long *extB,
+                      const char *ib, double beta, double *C, const long *extC, const char *ic) {
+    REF_TRY
+    auto make = [](const double *p, const long *e, const char *labels) {
+        const size_t r = std::strlen(labels);
+        DTensor t;
+        switch (r) {
+            case 2: t = DTensor(e[0], e[1]); break;
+            case 4: t = DTensor(e[0], e[1], e[2], e[3]); break;
+            case 6: t = DTensor(e[0], e[1], e[2], e[3], e[4], e[5]); break;
+            default: throw std::invalid_argument("ref_shim_contract: rank must be 2, 4 or 6");
+        }
+        std::memcpy(t.data(), p, sizeof(double) * t.size());
+        return t;
+    };
+    auto labels = [](const char *s) {
+        std::vector<int> v;
+        for (; *s; ++s) v.push_back((int) *s);
+        return v;
+    };
+    DTensor a = make(A, extA, ia), b = make(B, extB, ib), c = make(C, extC, ic);
+    btas::contract_labels(alpha, a, labels(ia), b, labels(ib), beta, c, labels(ic));
+    put(c, C);
+    REF_CATCH
+}
+
 int ref_transform_ao_mo(const double *ao, const double *C1, const double *C2, int n, double *out) {
     REF_TRY
     put(transform_ao_mo(t4(n, n, n, n, ao), mat(n, n, C1), mat(n, n, C2)), out);

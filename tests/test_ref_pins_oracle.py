@@ -50,6 +50,39 @@ def amplitudes(o, v, seed):
     return 0.1 * rng.standard_normal((o, v)), 0.05 * rng.standard_normal((o, o, v, v))
 
 
+# every distinct index pattern of the reference's 71 btas::contract call sites (integrals.cpp:121-129, cc.cpp:194-523)
+CONTRACT_PATTERNS = [
+    ("pqrs", "sl", "pqrl"), ("pqrl", "rk", "pqkl"), ("qj", "pqkl", "pjkl"), ("pi", "pjkl", "ijkl"),
+    ("me", "ma", "ae"), ("mf", "mafe", "ae"), ("mnaf", "mnef", "ae"), ("ie", "me", "mi"), ("ne", "mnie", "mi"),
+    ("inef", "mnef", "mi"), ("nf", "mnef", "me"), ("je", "mnie", "mnij"), ("ie", "mnje", "mnij"),
+    ("ijef", "mnef", "mnij"), ("mb", "amef", "abef"), ("ma", "bmef", "abef"), ("mnab", "mnef", "abef"),
+    ("jf", "mbef", "mbej"), ("nb", "mnej", "mbej"), ("jnfb", "mnef", "mbej"), ("jfnb", "mnef", "mbej"),
+    ("ie", "ae", "ia"), ("ma", "mi", "ia"), ("imae", "me", "ia"), ("nf", "naif", "ia"), ("imef", "maef", "ia"),
+    ("mnae", "nmei", "ia"), ("ijae", "be", "ijab"), ("ijbe", "ae", "ijab"), ("mb", "me", "be"),
+    ("imab", "mj", "ijab"), ("jmab", "mi", "ijab"), ("je", "me", "jm"), ("imab", "jm", "ijab"),
+    ("mnab", "mnij", "ijab"), ("ijef", "abef", "ijab"), ("imae", "mbej", "ijab"), ("jmae", "mbei", "ijab"),
+    ("imbe", "maej", "ijab"), ("jmbe", "maei", "ijab"), ("iema", "mbje", "ijab"), ("jemb", "maie", "ijab"),
+    ("ie", "abej", "ijab"), ("je", "abei", "ijab"), ("ma", "mbij", "ijab"), ("mb", "maij", "ijab"),
+    ("jkae", "eibc", "ijkabc"), ("jkce", "eiba", "ijkabc"), ("imbc", "majk", "ijkabc"), ("kmba", "mcji", "ijkabc")]
+
+
+@pytest.mark.parametrize("pattern", CONTRACT_PATTERNS)
+def test_shim_contract_is_einsum(pattern):
+    """What stays restated in the compiled reference is BTAS' contract itself (the library is absent).  The shim's
+    implementation (permute -> GEMM -> permute, like BTAS) against numpy.einsum and against the oracle's engine on
+    every index pattern the reference uses, with alpha/beta accumulation."""
+    ia, ib, ic = pattern
+    rng = np.random.default_rng(sum(ord(ch) * (q + 1) for q, ch in enumerate("".join(pattern))))
+    ext = {l: (4 if l in "ijkmn" else 6) for l in "abcefijklmnpqrs"}
+    if "p" in ia + ib + ic:
+        ext.update({l: 5 for l in "pqrslijk"})
+    A, B, C0 = (rng.standard_normal([ext[l] for l in lab]) for lab in (ia, ib, ic))
+    got = ref.shim_contract(0.7, A, ia, B, ib, -0.3, C0, ic)
+    want = -0.3 * C0 + 0.7 * np.einsum(f"{ia},{ib}->{ic}", A, B)
+    assert np.max(np.abs(got - want)) < 1e-13
+    assert np.max(np.abs(got - orc.contract(0.7, A, ia, B, ib, -0.3, C0, ic))) < 1e-13
+
+
 def test_transform_ao_mo_and_to_so(staged):
     case, st = staged
     uhf = "Ca" in case

@@ -219,3 +219,16 @@ def test_oracle_on_host_substrate_matches_reference_fixture(name):
     assert st["iters"] == g["cc_iters"]
     if "e_t" in st:
         assert abs(st["e_t"] - g["e_t"]) < 1e-10
+
+
+def test_host_uhf_scf_matches_reference_scf():
+    """The product's host SCF substrate (qc-p2_b200/host/hf.cpp) vs the reference's UHF (hf.cpp:462-579, compiled) on
+    NH2/cc-pVDZ: same SCF energy, orbital energies and -- up to the arbitrary sign of each MO -- coefficients."""
+    g = json.load(open(GOLDEN))["nh2_ccpvdz_uhf"]
+    b = np.load(os.path.join(ROOT, "tests", "golden", "reference_nh2_boundary.npz"))
+    case = molecule_case(**MOLECULES["nh2_ccpvdz_uhf"])
+    assert (case["n"], case["no"], case["nv"]) == (g["n"], g["no"], g["nv"])
+    assert abs(case["e_scf"] - g["e_scf"]) < 1e-10
+    assert np.max(np.abs(case["eps_a"] - b["eps_a"])) < 1e-9 and np.max(np.abs(case["eps_b"] - b["eps_b"])) < 1e-9
+    for mine, theirs in ((case["Ca"], b["Ca"]), (case["Cb"], b["Cb"])):
+        assert np.max(np.abs(np.abs(mine) - np.abs(theirs))) < 1e-7

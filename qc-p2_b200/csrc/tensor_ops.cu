@@ -195,11 +195,22 @@ __global__ void __launch_bounds__(256) to_so_kernel(const double *__restrict__ a
             for (int L = lane; L < n; L += 32) row[L] = make_double2(0.0, 0.0);// never-written spin patterns (zero-initialised in the reference)
             continue;
         }
-        for (int L = lane; L < n; L += 32) {
-            double val = p_ikj[L];
-            if (p_jki) val -= p_jki[L];
-            val *= sign;
-            row[L] = slot ? make_double2(0.0, val) : make_double2(val, 0.0);
+        for (int L0 = lane; L0 < n; L0 += 128) {// four independent load pairs in flight per lane before the first store
+            double va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int L = L0 + 32 * u;
+                va[u] = L < n ? p_ikj[L] : 0.0;
+                vb[u] = (p_jki && L < n) ? p_jki[L] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int L = L0 + 32 * u;
+                if (L < n) {
+                    const double val = sign * (va[u] - vb[u]);
+                    row[L] = slot ? make_double2(0.0, val) : make_double2(val, 0.0);
+                }
+            }
         }
     }
 }

@@ -394,3 +394,22 @@ def test_t_mgpu_entry_point_on_a_single_rank_communicator():
     c.comm_destroy()
     assert c.comm_rank() == (0, 1)
     c.close()
+
+
+def test_post_hf_mgpu_on_a_single_rank_communicator():
+    """qcp2_post_hf_mgpu (collective fused pipeline) at world size 1: the same numbers as qcp2_post_hf; ranks 2..8 with
+    sharded CCSD products are checked by tools/mgpu_ccsd_check.py under torchrun (profiles/r1_mgpu_ccsd_check_*)."""
+    c = qcp2_b200.Context(0)
+    c.comm_init(qcp2_b200.comm_unique_id(), 1, 0)
+    for case in (rhf_case(6, 2, 81), uhf_case(5, 3, 2, 82)):
+        uhf = "Ca" in case
+        Ca = case["Ca"] if uhf else case["C"]
+        ea, eb = (case["eps_a"], case["eps_b"]) if uhf else (case["eps"], None)
+        a = c.post_hf(case["ao"], Ca, case.get("Cb"), ea, eb, case["no"], case["nv"], uhf=uhf, stages=3, maxiter=60, cc_conv=1e-12)
+        b = c.post_hf_mgpu(case["ao"], Ca, case.get("Cb"), ea, eb, case["n"], case["no"], case["nv"], uhf=uhf, stages=3, maxiter=60,
+                           cc_conv=1e-12, root=0)
+        for k in ("e_mp2", "e_ccsd", "e_t"):
+            assert a[k] == b[k], k
+        assert a["iters"] == b["iters"] and np.array_equal(a["e_hist"], b["e_hist"])
+    assert c.sharded_gemms == 0
+    c.close()

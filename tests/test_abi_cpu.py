@@ -48,3 +48,26 @@ def test_product_path_does_not_reference_oracle():
             if f.endswith((".cu", ".cuh", ".cpp", ".h", ".py", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
+
+
+def test_p2_driver_refuses_to_run_without_gpus(tmp_path):
+    """The C++ host mirror has no CPU path either: `P2` fails cleanly without a device, and `P2 --gpus N` checks
+    the visible GPU count (in a throw-away child, so the parent can still fork its workers) before spawning anything."""
+    import json
+    import subprocess
+
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is exercised on the CPU box")
+    root = os.path.dirname(os.path.dirname(qcp2_b200.HEADER_PATH))
+    exe = os.path.join(root, "qc-p2_b200", "bin", "P2")
+    assert os.path.exists(exe), "build qc-p2_b200/host first (__graft_entry__.build())"
+    cfg = json.load(open(os.path.join(root, "input.json")))
+    inp = tmp_path / "input.json"
+    inp.write_text(json.dumps(cfg))
+    multi = subprocess.run([exe, "--gpus", "2", str(inp)], cwd=root, capture_output=True, text=True, timeout=120)
+    assert multi.returncode != 0 and "GPU(s) visible" in multi.stderr
+    single = subprocess.run([exe, str(inp)], cwd=root, capture_output=True, text=True, timeout=300)
+    assert single.returncode != 0 and "no CPU fallback" in single.stderr
+    usage = subprocess.run([exe], cwd=root, capture_output=True, text=True, timeout=30)
+    assert usage.returncode == 2 and "usage" in usage.stderr

@@ -232,3 +232,29 @@ def test_host_uhf_scf_matches_reference_scf():
     assert np.max(np.abs(case["eps_a"] - b["eps_a"])) < 1e-9 and np.max(np.abs(case["eps_b"] - b["eps_b"])) < 1e-9
     for mine, theirs in ((case["Ca"], b["Ca"]), (case["Cb"], b["Cb"])):
         assert np.max(np.abs(np.abs(mine) - np.abs(theirs))) < 1e-7
+
+
+def test_reference_vs_oracle_over_random_shapes():
+    """Property test (hypothesis): for random small (n, occupation, seed), RHF and as-written UHF, five Jacobi
+    iterations of the reference's own chain and of the oracle restatement give the same MP2 / CCSD / (T) numbers."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(n=st.integers(2, 5), frac=st.floats(0.2, 0.8), seed=st.integers(0, 10 ** 6), uhf=st.booleans())
+    def check(n, frac, seed, uhf):
+        nd = max(1, min(n - 1, int(round(frac * n))))
+        if uhf:
+            nb = max(1, nd - 1) if nd > 1 else 1
+            case = uhf_case(n, nd, nb, seed) if nd + nb < 2 * n else rhf_case(n, nd, seed)
+        else:
+            case = rhf_case(n, nd, seed)
+        r = ref.post_hf(case, maxiter=5, conv=1e-14)
+        o = oracle_pipeline(case, maxiter=5, conv=1e-14)
+        scale = max(1.0, abs(o["e_ccsd"]), abs(o["e_t"]))
+        assert abs(r["e_mp2"] - o["e_mp2"]) <= 1e-13 * max(1.0, abs(o["e_mp2"]))
+        # the reference reports the last iteration number it printed (cc.cpp:437): maxiter - 1 when the cap is hit
+        assert r["iters"] == min(o["iters"], 4)
+        assert abs(r["e_ccsd"] - o["e_ccsd"]) <= 1e-12 * scale and abs(r["e_t"] - o["e_t"]) <= 1e-12 * scale
+
+    check()

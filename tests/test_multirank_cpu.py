@@ -65,3 +65,36 @@ def test_rank_partition_covers_every_triple_once():
                 seen[first::stride] += 1
                 assert qcp2_b200.shard.rank_count(n, r, world) == len(range(first, n, stride))
             assert np.all(seen == 1)
+
+
+def _bootstrap_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import qcp2_b200
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # the host half of Context.comm_init_from_torch: rank 0 makes the NCCL id, the process group hands it round
+    box = [qcp2_b200.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    out[rank] = bytes(box[0])
+    dist.destroy_process_group()
+
+
+def test_two_rank_bootstrap_of_the_library_communicator_id():
+    """qcp2_comm_get_unique_id needs no GPU: the 128-byte NCCL bootstrap id made by rank 0 reaches every rank unchanged
+    (qcp2_comm_init itself is collective over GPUs and is exercised by tools/mgpu_check.py on the GPU box)."""
+    import ctypes
+
+    import qcp2_b200
+    try:
+        qcp2_b200.comm_unique_id()
+    except qcp2_b200.QCP2Error:
+        import pytest
+        pytest.skip("libnccl.so.2 is not loadable here")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_bootstrap_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] == out[1] and len(out[0]) == qcp2_b200.COMM_ID_BYTES and any(out[0])
+    # a too-small buffer is refused instead of overrun
+    small = ctypes.create_string_buffer(16)
+    assert qcp2_b200.load_library().qcp2_comm_get_unique_id(small, 16) != 0

@@ -26,6 +26,21 @@ import sys
 import threading
 import time
 
+
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# The CPU legs (--impl reference, cpu_baseline) must use every host core.  torch.distributed.run exports
+# OMP_NUM_THREADS=1 to its workers, and OpenBLAS / libgomp read the variable when they are loaded, so it is
+# overridden here, before numpy is imported (the N>1 reference arm ran on one thread).
+if any(a == "reference" or a.endswith("=reference") for a in sys.argv[1:]):
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_host_cores())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -44,7 +59,8 @@ def make_config(o, v, world):
     return {"workload": f"(T) energy, synthetic closed-shell o={o} v={v} (BASELINE.json configs[4]), antisymmetrised "
                         "counter-based inputs, i<j<k triples dealt round-robin over ranks",
             "o": o, "v": v, "triples_total": nt, "alg_flops_per_triple": t_flops_per_triple(o, v),
-            "parallelism": f"triples x{world}"}
+            "parallelism": f"triples x{world}",
+            "l2": "each triple streams 0.84 GB of B rows (>> 126 MB L2); no flush needed"}
 
 
 def parse():
@@ -140,12 +156,15 @@ class CpuTriples:
 
 
 def host_threads():
+    """Threads the BLAS behind numpy actually uses (raised to every host core if something capped it)."""
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
+        if max((p.get("num_threads", 1) for p in threadpool_info()), default=1) < _host_cores():
+            threadpool_limits(_host_cores())  # stays in force for the rest of the process
         n = max((p.get("num_threads", 1) for p in threadpool_info()), default=1)
         return int(n)
     except Exception:
-        return os.cpu_count() or 1
+        return _host_cores()
 
 
 def run_reference(args, rank):
@@ -162,6 +181,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     o, v = args.o, args.v
+    cores = host_threads()
     cpu = CpuTriples(o, v)
     for _ in range(min(args.warmup, 1)):  # one warm-up triple is enough to spin up the BLAS threads
         cpu.run(1)
@@ -174,8 +194,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(make_config(o, v, args.gpus), triples_per_step=args.cpu_triples),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": host_threads(), "kind": "port",
+            "config": make_config(o, v, args.gpus), "arm": {"triples_per_step": args.cpu_triples},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{args.cpu_triples} sampled i<j<k triples per step x {args.steps} steps of the o={o}/v={v} "
                                        "workload; per-triple M=v,N=v(v-1)/2,K=3(v+o) six DGEMMs on numpy/OpenBLAS from pre-packed slabs + OpenMP a<b<c energy sum"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -211,6 +231,46 @@ def reference_own_code_sample(o=8, v=40):
 # ----------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------
+T_GEMM_PROFILES = ("profiles/r2_t_gemm_tma_ncu_full.txt", "profiles/r1_t_gemm_tma_ncu_full.txt")
+E2E_N1_RECORDS = ("profiles/r2_bench_n1.json", "profiles/r1_bench_n1_final.json")
+
+
+def tracked_gemm_traffic():
+    """DRAM bytes per triple of the (T) GEMM, read from the newest tracked `ncu --set full` summary
+    (tools/ncu_summary.py output): dram__bytes_read.sum + dram__bytes_write.sum of one launch divided by the
+    triples of that launch (grid.z).  Returns (bytes_per_triple, file) or (None, None)."""
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for rel in T_GEMM_PROFILES:
+        try:
+            txt = open(os.path.join(ROOT, rel)).read()
+        except OSError:
+            continue
+        for block in txt.split("kernel:")[1:]:
+            if "t_gemm_tma_kernel" not in block.splitlines()[0]:
+                continue
+            grid = re.search(r"grid/block:\s*\((\d+),\s*(\d+),\s*(\d+)\)", block)
+            rd = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", block)
+            wr = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", block)
+            if grid and rd and wr:
+                total = float(rd.group(1)) * unit[rd.group(2)] + float(wr.group(1)) * unit[wr.group(2)]
+                return total / max(int(grid.group(3)), 1), rel
+    return None, None
+
+
+def committed_n1_e2e():
+    """E(T) and wall time of the whole job on ONE GPU from the newest tracked record (the bit-identity and
+    strong-scaling yardsticks for the N>1 lines)."""
+    for rel in E2E_N1_RECORDS:
+        try:
+            rec = json.loads(open(os.path.join(ROOT, rel)).read().strip().splitlines()[-1])
+            if rec.get("n_gpus") == 1 and rec.get("e2e"):
+                return rec["e2e"]["e_t"], rec["e2e"]["seconds"], rec["config"]["o"], rec["config"]["v"], rel
+        except (OSError, ValueError, KeyError, IndexError):
+            continue
+    return None, None, None, None, None
+
+
 def cublas_fp64_peak(torch, n=8192):
     """FP64 roofline denominator measured live: cuBLAS DGEMM via torch.matmul (yardstick only)."""
     a = torch.randn(n, n, dtype=torch.float64, device="cuda")
@@ -405,13 +465,13 @@ def main():
     # ---- roofline of the dominant kernel (the segmented-K DMMA GEMM), this rank
     peak_burst, peak_sus = (0.0, 0.0) if args.no_peak else cublas_fp64_peak(torch)
     achieved = done_local * fpt / gemm_s / 1e12 if gemm_s > 0 else 0.0
-    # DRAM bytes per triple of the GEMM from the committed ncu --set full capture
-    # (profiles/r1_t_gemm_tma_ncu_full.txt: 2.745 GB read + 0.751 GB written for a 3-triple launch);
+    # DRAM bytes per triple of the GEMM, read from the tracked ncu --set full summary (captured at o=40, v=400);
     # algorithmic bytes per triple: B rows 843 MB + X 255 MB + A 5 MB = 1.10 GB
-    dram_per_triple = (2.744980e9 + 0.750871e9) / 3.0 if (o, v) == (40, 400) else None
+    dram_per_triple, traffic_file = tracked_gemm_traffic() if (o, v) == (40, 400) else (None, None)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_sus, "unit": "TFLOP/s",
                 "frac": achieved / peak_sus if peak_sus else None,
                 "traffic": dram_per_triple * done_local / max(gemm_n, 1) if dram_per_triple else None,
+                "traffic_source": traffic_file,
                 "kernel": "t_gemm_tma_kernel (80x256x16 CTA tile, 4-stage cp.async.bulk/mbarrier ring, 8 DMMA.8x8x4 consumer warps)",
                 "avg_launch_ms": 1e3 * gemm_s / max(gemm_n, 1),
                 "launches": gemm_n, "alg_flops_per_launch": done_local * fpt / max(gemm_n, 1),
@@ -452,7 +512,14 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": nt * fpt / float(dt[0]) / 1e12, "unit": UNIT, "h2d_bytes_per_step": h2d if rank == 0 else 0,
+        ref_e, ref_s, ref_o, ref_v, ref_file = committed_n1_e2e()
+        comparable = ref_e is not None and (ref_o, ref_v) == (o, v)
+        e2e = {"value": nt * fpt / float(dt[0]) / 1e12, "unit": UNIT,
+               # E(T) of the whole job against the committed one-GPU value, bit for bit (fixed triple->slot map + fixed-order sum)
+               "e_t_matches_n1": (e_job == ref_e) if comparable else None, "e_t_n1": ref_e if comparable else None,
+               # whole-job strong scaling: T(1 GPU, committed record) / (N x T(N GPUs, this run)); at N=1 it compares boxes
+               "strong_scaling_efficiency": ref_s / (world * float(dt[0])) if comparable else None,
+               "n1_record": ref_file if comparable else None, "h2d_bytes_per_step": h2d if rank == 0 else 0,
                "d2h_bytes_per_step": 8 * (nt + 1), "steps": 1, "seconds": float(dt[0]), "e_t": e_job,
                "what": "whole (T) job (all %d triples) via qcp2_ccsd_t with pinned host buffers" % nt if world == 1 else
                        "whole (T) job via qcp2_ccsd_t_mgpu: rank-0 pinned host buffers -> H2D -> ncclBroadcast -> round-robin triples -> ncclAllReduce"}
@@ -479,8 +546,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": dict(make_config(o, v, world), triples_per_rank_per_step=B,
-                               l2="each triple streams 0.84 GB of B rows (>> 126 MB L2); no flush needed"),
+                "config": make_config(o, v, world), "arm": {"triples_per_rank_per_step": B},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "ccsd": ccsd, "energy_checksum": energy_acc}
         emit(line)

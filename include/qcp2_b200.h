@@ -159,7 +159,10 @@ int qcp2_comm_allgather(qcp2_ctx *ctx, const double *dev_send, double *dev_recv,
  * triples {r, r+W, r+2W, ...} of the mode's enumeration, one ncclAllReduce combines the
  * per-triple energy vector and every rank returns the same, fixed-order sum in *energy:
  * bit-identical to qcp2_ccsd_t for any number of ranks.  e_triples (host, qcp2_ccsd_t_count()
- * doubles) may be NULL. */
+ * doubles) may be NULL.  The ROOT's `mode` decides for everyone (it travels in the broadcast header), and a
+ * failure on any rank before the payload broadcasts makes every rank return status 1 together.
+ * Host buffers should be pinned (cudaHostAlloc / cudaHostRegister): pageable memory is staged synchronously by
+ * the driver, which serialises the <vo||vv> upload with the compute it is meant to overlap. */
 int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
                      const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode, int root,
                      double *e_triples, double *energy);
@@ -167,10 +170,13 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
 /* Fused MP2 -> CCSD -> (T) across the communicator (collective; same n, o, v, uhf, stages, maxiter, conv, root
  * on every rank).  Rank `root` supplies the boundary inputs of qcp2_post_hf (host or device pointers per its pointer
  * mode), the others may pass NULL.  The inputs are broadcast; AO->MO, <pq||rs>, MP2 and the slicing run replicated
- * (milliseconds); in every CCSD iteration the large products (particle-particle ladder over occupied pairs i<j, ring
- * and W_mbej products, tau.<am||ef>) are split by rows over the ranks and re-assembled with one ncclBroadcast per
- * rank (an all-gather with unequal counts), everything else is replicated, so all ranks hold identical amplitudes; the
- * (T) triples are dealt round-robin and combined with one ncclAllReduce.  Every rank returns the same energies.
+ * (milliseconds); in every CCSD iteration each product above 2e9 flop (the packed particle-particle ladder, the ring
+ * and W_mbej products, tau.<am||ef>) is split over the ranks along its LONGER free dimension -- the ladder over the
+ * a<b columns of <vv||vv>, so the big operand is streamed once in total -- each rank writes its slab into a W x R
+ * row workspace and ONE in-place ncclAllGather re-assembles the product on every rank (csrc/dgemm.cu); everything
+ * else is replicated, so all ranks hold identical amplitudes; the (T) triples are dealt round-robin and combined with
+ * one ncclAllReduce.  Every rank returns the same energies.  If any rank fails before the first exchange (bad
+ * arguments on the root, staging out of memory) every rank returns status 1 -- no rank is left inside a collective.
  * QCP2_CCSD_NO_SHARD=1 keeps the iteration replicated.  qcp2_sharded_gemms: products split so far on this context. */
 int qcp2_post_hf_mgpu(qcp2_ctx *ctx, const double *ao_ints, const double *Ca, const double *Cb, const double *eps_a,
                       const double *eps_b, int n, int o, int v, int uhf, int stages, int maxiter, double conv, int root,

@@ -639,7 +639,6 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
         QCP2_REQUIRE(energy && o >= 0 && v >= 0, "(T) mgpu: null argument");
         QCP2_REQUIRE(root >= 0 && root < cm.nranks, "(T) mgpu: root out of range");
         const bool is_root = cm.rank == root;
-        if (is_root) QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v, "(T) mgpu: the root rank must supply every tensor");
         Trace tr(c, "qcp2_ccsd_t_mgpu");
         const long long O = o, V = v;
         enum { kT1, kT2, kG, kW, kX, kEo, kEv };
@@ -661,34 +660,48 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
                 dev[k] = scratch[k].p;
             }
         };
-        for (int k = 0; k < 7; ++k)
-            if (k != kW) place(k);
-        // header from the root: [0] evaluation mode, [1] 1 = <vo||vv> is streamed from the root's host tensor.
-        // The root's pointer mode decides (the other ranks may be in either mode).
-        DBuf hdr(c, 2);
-        double hh[2] = {0.0, 0.0};
-        if (is_root) {
-            int m = mode;
-            bool streamed = false;
-            if (stream_allowed(c, mode, o, v) &&
-                (mode == QCP2_T_SYMMETRIC || t_select_mode(c, dev[kT2], dev[kG], nullptr, dev[kX], o, v) == QCP2_T_SYMMETRIC))
-                streamed = true, m = QCP2_T_SYMMETRIC;
-            if (!streamed) {
-                place(kW);
-                if (m == QCP2_T_AUTO) m = t_select_mode(c, dev[kT2], dev[kG], dev[kW], dev[kX], o, v);
+        // header from the root: [0] evaluation mode, [1] 1 = <vo||vv> is streamed from the root's host tensor,
+        // [2] the mode the root was CALLED with (the other ranks' `mode` argument is ignored, so a mismatch cannot
+        // send the ranks down different collective sequences).  The root's pointer mode decides streaming.
+        // Everything that can fail before the first payload collective (argument checks, staging, the symmetry
+        // probe) runs inside this try block on every rank; the outcomes are then summed over the ranks so that all
+        // of them leave together instead of one rank throwing while the others block in ncclBroadcast.
+        DBuf hdr(c, 4);
+        double hh[4] = {0.0, 0.0, 0.0, 0.0};
+        std::string local_err;
+        try {
+            if (is_root) QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v, "(T) mgpu: the root rank must supply every tensor");
+            for (int k = 0; k < 7; ++k)
+                if (k != kW) place(k);
+            if (is_root) {
+                int m = mode;
+                bool streamed = false;
+                if (stream_allowed(c, mode, o, v) &&
+                    (mode == QCP2_T_SYMMETRIC || t_select_mode(c, dev[kT2], dev[kG], nullptr, dev[kX], o, v) == QCP2_T_SYMMETRIC))
+                    streamed = true, m = QCP2_T_SYMMETRIC;
+                if (!streamed) {
+                    place(kW);
+                    if (m == QCP2_T_AUTO) m = t_select_mode(c, dev[kT2], dev[kG], dev[kW], dev[kX], o, v);
+                }
+                QCP2_REQUIRE(m == QCP2_T_LITERAL || m == QCP2_T_SYMMETRIC, "(T) mgpu: unknown evaluation mode");
+                hh[0] = (double) m, hh[1] = streamed ? 1.0 : 0.0, hh[2] = (double) mode;
             }
-            hh[0] = (double) m, hh[1] = streamed ? 1.0 : 0.0;
-            QCP2_CUDA(cudaMemcpyAsync(hdr.p, hh, 16, cudaMemcpyHostToDevice, c.stream));
             c.sync();
+        } catch (const std::exception &e) {
+            local_err = e.what();
+            cudaGetLastError();
         }
-        comm_broadcast(c, cm, hdr.p, 2, root);
+        comm_agree(c, cm, local_err, "(T) mgpu");
+        if (is_root) QCP2_CUDA(cudaMemcpyAsync(hdr.p, hh, 32, cudaMemcpyHostToDevice, c.stream));
+        comm_broadcast(c, cm, hdr.p, 4, root);
         for (int k = 0; k < 7; ++k)
             if (k != kW) comm_broadcast(c, cm, dev[k], sizes[k], root);
-        QCP2_CUDA(cudaMemcpyAsync(hh, hdr.p, 16, cudaMemcpyDeviceToHost, c.stream));
+        QCP2_CUDA(cudaMemcpyAsync(hh, hdr.p, 32, cudaMemcpyDeviceToHost, c.stream));
         c.sync();
         tr.mark("stage + broadcast the small inputs");
         int m = (int) hh[0];
         bool streamed = hh[1] != 0.0;
+        const int root_mode = (int) hh[2];// what the root was asked for; identical on every rank
         QCP2_REQUIRE(m == QCP2_T_LITERAL || m == QCP2_T_SYMMETRIC, "(T) mgpu: mode broadcast failed");
         TEval E;
         bool done = false;
@@ -698,14 +711,22 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
             t_evaluate(c, E, dev[kT1], dev[kT2], dev[kG], nullptr, dev[kX], dev[kEo], dev[kEv], o, v, QCP2_T_SYMMETRIC, &ts, cm.rank,
                        cm.nranks, -1, true, tr);
             done = true;
-            if (mode == QCP2_T_AUTO) {// the slab-wise <vo||vv> check, known to every rank through the broadcast
+            if (root_mode == QCP2_T_AUTO) {// the slab-wise <vo||vv> check, known to every rank through the broadcast
                 double defect, mx;
                 t_plan_vovv_defect(*E.plan, &defect, &mx);
                 if (!(defect <= 1e-10 * mx)) done = false, m = QCP2_T_LITERAL, E = TEval();
             }
         }
         if (!done) {
-            if (!dev[kW]) place(kW);
+            std::string err;
+            try {
+                if (!dev[kW]) place(kW);
+                c.sync();
+            } catch (const std::exception &e) {
+                err = e.what();
+                cudaGetLastError();
+            }
+            comm_agree(c, cm, err, "(T) mgpu, <vo||vv> staging");
             comm_broadcast(c, cm, dev[kW], sizes[kW], root);
             tr.mark("stage + broadcast <vo||vv>");
             t_evaluate(c, E, dev[kT1], dev[kT2], dev[kG], dev[kW], dev[kX], dev[kEo], dev[kEv], o, v, m, nullptr, cm.rank, cm.nranks, -1,
@@ -778,10 +799,8 @@ void post_hf_impl(Ctx &c, Comm *cm, int root, const double *ao_ints, const doubl
                   double *e_ccsd, double *e_t, int *iters, double *e_hist, double *T1, double *T2) {
     const bool multi = cm && cm->nranks > 1;
     const bool is_root = !multi || cm->rank == root;
-    if (is_root) QCP2_REQUIRE(ao_ints && Ca && eps_a, "post_hf: null argument");
     QCP2_REQUIRE(e_mp2 && n >= 1, "post_hf: null argument");
     QCP2_REQUIRE(stages >= 1 && stages <= 3, "post_hf: stages must be 1, 2 or 3");
-    if (uhf && is_root) QCP2_REQUIRE(Cb && eps_b, "post_hf: UHF needs Cb and eps_b");
     if (stages >= 2) QCP2_REQUIRE(e_ccsd && maxiter >= 0, "post_hf: CCSD outputs missing");
     if (stages >= 3) QCP2_REQUIRE(e_t, "post_hf: (T) output missing");
     const long long n4 = ipow4(n), O = o, V = v, o2v2 = O * O * V * V;
@@ -796,9 +815,22 @@ void post_hf_impl(Ctx &c, Comm *cm, int root, const double *ao_ints, const doubl
         in.p = scratch[slot].p;
         return in;
     };
-    In ao = place(ao_ints, n4, 0), ca = place(Ca, (long long) n * n, 1), ea = place(eps_a, n, 2);
-    In cb = uhf ? place(Cb, (long long) n * n, 3) : In();
-    In eb = uhf ? place(eps_b, n, 4) : In();
+    In ao, ca, ea, cb, eb;
+    {// root-only checks and the staging can fail on one rank only: agree on the outcome before the first broadcast
+        std::string err;
+        try {
+            if (is_root) QCP2_REQUIRE(ao_ints && Ca && eps_a, "post_hf: null argument");
+            if (uhf && is_root) QCP2_REQUIRE(Cb && eps_b, "post_hf: UHF needs Cb and eps_b");
+            ao = place(ao_ints, n4, 0), ca = place(Ca, (long long) n * n, 1), ea = place(eps_a, n, 2);
+            if (uhf) cb = place(Cb, (long long) n * n, 3), eb = place(eps_b, n, 4);
+            if (multi) c.sync();
+        } catch (const std::exception &e) {
+            err = e.what();
+            cudaGetLastError();
+        }
+        if (multi) comm_agree(c, *cm, err, "post_hf_mgpu");
+        else if (!err.empty()) throw Error(err);
+    }
     if (multi) {
         comm_broadcast(c, *cm, const_cast<double *>(ao.p), n4, root);
         comm_broadcast(c, *cm, const_cast<double *>(ca.p), (long long) n * n, root);

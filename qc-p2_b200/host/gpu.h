@@ -5,6 +5,7 @@
 #pragma once
 #include <sys/types.h>
 #include <sys/wait.h>
+#include <signal.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -131,10 +132,26 @@ inline int mgpu_shutdown() {
             if (write(fd, &m, sizeof(m)) != (ssize_t) sizeof(m)) bad = 1;
             close(fd);
         }
+        // a worker that is still inside a collective because rank 0 failed mid-way never reads the dismissal:
+        // wait a bounded time (QCP2_WORKER_TIMEOUT_S, default 60 s), then kill it -- `P2 --gpus N` must exit
+        const char *tenv = getenv("QCP2_WORKER_TIMEOUT_S");
+        const double limit = tenv ? atof(tenv) : 60.0;
         for (pid_t p : s.pids) {
             int st = 0;
-            waitpid(p, &st, 0);
-            if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) bad = 1;
+            double waited = 0.0;
+            pid_t r = 0;
+            while ((r = waitpid(p, &st, WNOHANG)) == 0 && waited < limit) {
+                usleep(20000);
+                waited += 0.02;
+            }
+            if (r == 0) {
+                fprintf(stderr, "P2: worker %d did not exit within %.0f s, killing it\n", (int) p, limit);
+                kill(p, SIGKILL);
+                waitpid(p, &st, 0);
+                bad = 1;
+            } else if (r < 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+                bad = 1;
+            }
         }
         s.to_worker.clear(), s.pids.clear();
     }

@@ -219,6 +219,16 @@ int qcp2_contract(qcp2_ctx *ctx, double alpha, const double *A, const long long 
  * transA == 0: A is [M,K] (lda >= K), else A is [K,M]; transB == 0: B is [K,N], else [N,K]. */
 int qcp2_dgemm(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A,
                long long lda, const double *B, long long ldb, double beta, double *C, long long ldc);
+/* The same product with device pointers only, a strided batch, a forced kernel choice and device timing (tests and
+ * tuning tools): tile < 0 lets the library choose; 0..4 force the warp-specialised TMA kernel's CTA tile
+ * (80x256, 48x256, 16x256, 64x64, 112x128), +8 runs the transposed problem C^T = B^T A^T on that tile; k_splits > 0
+ * forces the split-K factor; the product is launched `reps` times and *seconds (may be NULL) receives the mean device
+ * time of one launch.  Operands that are not 16-byte aligned take the cp.async kernel regardless of `tile`. */
+int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A, long long lda,
+                  const double *B, long long ldb, double beta, double *C, long long ldc, int batch, long long strideA,
+                  long long strideB, long long strideC, int tile, int k_splits, int reps, double *seconds);
+/* products run so far on the warp-specialised TMA kernel (return value) and on the cp.async kernel (*legacy) */
+long long qcp2_gemm_counts(const qcp2_ctx *ctx, long long *legacy);
 /* counter-based synthetic (T) inputs of SURVEY.md section 8d, generated on the device
  * (device pointers regardless of pointer mode) */
 int qcp2_synth_t_inputs(qcp2_ctx *ctx, int o, int v, unsigned long long seed, double *T1, double *T2, double *oovv,

@@ -115,10 +115,20 @@ int qcp2_create(int device, qcp2_ctx **out) {
         ctx->c.sm_count = prop.multiProcessorCount;
         QCP2_CUDA(cudaStreamCreateWithFlags(&ctx->c.own_stream, cudaStreamNonBlocking));
         ctx->c.stream = ctx->c.own_stream;
-        cudaMemPool_t pool;
-        QCP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        unsigned long long keep = ~0ULL;// keep freed workspace cached in the pool
-        QCP2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // a private stream-ordered pool: freed workspace stays cached in it (release threshold = max) and goes
+        // back to the driver in qcp2_destroy; the device's default pool is left untouched
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        QCP2_CUDA(cudaMemPoolCreate(&ctx->c.pool, &props));
+        unsigned long long keep = ~0ULL;
+        QCP2_CUDA(cudaMemPoolSetAttribute(ctx->c.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        // split-K tile counters of the warp-specialised GEMM (zero between launches)
+        ctx->c.ws_counters_cap = 1 << 16;
+        QCP2_CUDA(cudaMalloc(&ctx->c.ws_counters, (size_t) ctx->c.ws_counters_cap * sizeof(unsigned int)));
+        QCP2_CUDA(cudaMemset(ctx->c.ws_counters, 0, (size_t) ctx->c.ws_counters_cap * sizeof(unsigned int)));
     } catch (const std::exception &e) {
         fprintf(stderr, "qcp2_create: %s\n", e.what());
         return 1;
@@ -137,6 +147,11 @@ int qcp2_destroy(qcp2_ctx *ctx) {
         } catch (...) {
         }
         ctx->comm = nullptr;
+    }
+    if (ctx->c.ws_counters) cudaFree(ctx->c.ws_counters);
+    if (ctx->c.pool) {
+        cudaMemPoolTrimTo(ctx->c.pool, 0);
+        cudaMemPoolDestroy(ctx->c.pool);
     }
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.own_stream);
     delete ctx;
@@ -984,6 +999,37 @@ int qcp2_dgemm(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, doubl
         if (c.pointer_mode == QCP2_HOST) QCP2_CUDA(cudaMemcpyAsync(C, cp, (size_t) nc * 8, cudaMemcpyDeviceToHost, c.stream));
         c.sync();
     });
+}
+
+int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A, long long lda,
+                  const double *B, long long ldb, double beta, double *C, long long ldc, int batch, long long strideA,
+                  long long strideB, long long strideC, int tile, int k_splits, int reps, double *seconds) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(A && B && C && M >= 0 && N >= 0 && K >= 0 && batch >= 1, "dgemm_ex: bad argument");
+        QCP2_REQUIRE(c.pointer_mode == QCP2_DEVICE, "dgemm_ex: device pointers only");
+        GemmArgs g;
+        g.M = M, g.N = N, g.K = K, g.alpha = alpha, g.beta = beta, g.batch = batch;
+        g.A = A, g.lda = lda, g.strideA = strideA, g.B = B, g.ldb = ldb, g.strideB = strideB, g.C = C, g.ldc = ldc, g.strideC = strideC;
+        g.force_tile = tile, g.force_split = k_splits;
+        cudaEvent_t e0, e1;
+        QCP2_CUDA(cudaEventCreate(&e0));
+        QCP2_CUDA(cudaEventCreate(&e1));
+        QCP2_CUDA(cudaEventRecord(e0, c.stream));
+        for (int r = 0; r < std::max(reps, 1); ++r) gemm(c, g, !transA, !transB);
+        QCP2_CUDA(cudaEventRecord(e1, c.stream));
+        QCP2_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        if (seconds) *seconds = 1e-3 * ms / std::max(reps, 1);
+        c.sync();
+    });
+}
+
+long long qcp2_gemm_counts(const qcp2_ctx *ctx, long long *legacy) {
+    if (!ctx) return 0;
+    if (legacy) *legacy = ctx->c.legacy_gemms;
+    return ctx->c.ws_gemms;
 }
 
 int qcp2_synth_t_inputs(qcp2_ctx *ctx, int o, int v, unsigned long long seed, double *T1, double *T2, double *oovv,

@@ -64,16 +64,22 @@ struct Ctx {
     struct Comm *shard = nullptr;
     double shard_min_flops = 2.0e9;
     long long sharded_gemms = 0;
+    // split-K tile counters of the warp-specialised GEMM (dgemm_ws.cuh): zero between launches (the last CTA of a
+    // tile resets its counter), allocated with the context
+    unsigned int *ws_counters = nullptr;
+    int ws_counters_cap = 0;
+    long long ws_gemms = 0, legacy_gemms = 0;
 
-    double *alloc(size_t n_doubles) {
-        void *p = nullptr;
-        if (n_doubles == 0) n_doubles = 1;
-        QCP2_CUDA(cudaMallocAsync(&p, n_doubles * sizeof(double), stream));
-        return static_cast<double *>(p);
-    }
+    // workspace pool owned by this context (created in qcp2_create, trimmed and destroyed in qcp2_destroy): freed
+    // blocks stay cached here instead of in the device's default pool, so the library does not change the behaviour
+    // of other cudaMallocAsync users of the process
+    cudaMemPool_t pool = nullptr;
+
+    double *alloc(size_t n_doubles) { return static_cast<double *>(alloc_bytes((n_doubles ? n_doubles : 1) * sizeof(double))); }
     void *alloc_bytes(size_t n) {
         void *p = nullptr;
-        QCP2_CUDA(cudaMallocAsync(&p, n ? n : 1, stream));
+        if (pool) QCP2_CUDA(cudaMallocFromPoolAsync(&p, n ? n : 1, pool, stream));
+        else QCP2_CUDA(cudaMallocAsync(&p, n ? n : 1, stream));
         return p;
     }
     void free(void *p) {

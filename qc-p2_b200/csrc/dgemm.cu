@@ -4,6 +4,7 @@
 
 #include "comm.cuh"
 #include "dgemm.cuh"
+#include "dgemm_ws.cuh"
 #include "tensor_ops.cuh"
 
 namespace qcp2 {
@@ -30,6 +31,116 @@ struct TileChoice {
     int bm, bn;
     double eff;// rough per-CTA tensor-pipe efficiency of the tile shape
 };
+
+// ---- warp-specialised TMA path (dgemm_ws.cuh) ---------------------------------------------
+namespace {
+
+bool ws_eligible(const Ctx &ctx, const GemmArgs &g) {
+    static const bool off = getenv("QCP2_NO_WS_GEMM") != nullptr;
+    if (off || g.seg != nullptr || !ws_tma_available() || ctx.ws_counters == nullptr) return false;
+    if (g.K < 1) return false;
+    const bool batched = g.batch > 1;
+    if (!aligned16(g.A) || (g.lda & 1) || (batched && (g.strideA & 1))) return false;
+    if (!aligned16(g.B) || (g.ldb & 1) || (batched && (g.strideB & 1))) return false;
+    if (g.Cin && g.Cin != g.C && !g.row_off && (g.ldcin != g.ldc)) return false;// one addressing for C and Cin
+    return true;
+}
+
+void ws_dispatch(Ctx &ctx, int shape, const CUtensorMap &ta, const CUtensorMap &tb, const WsGemmArgs &w, bool a_kc, bool b_nc) {
+    switch (shape) {
+        case WS_80x256: ws_launch_80x256(ctx, ta, tb, w, a_kc, b_nc); break;
+        case WS_48x256: ws_launch_48x256(ctx, ta, tb, w, a_kc, b_nc); break;
+        case WS_16x256: ws_launch_16x256(ctx, ta, tb, w, a_kc, b_nc); break;
+        case WS_64x64: ws_launch_64x64(ctx, ta, tb, w, a_kc, b_nc); break;
+        default: ws_launch_112x128(ctx, ta, tb, w, a_kc, b_nc); break;
+    }
+}
+
+// runs g on the warp-specialised kernel: tile `shape`, optionally as the transposed problem C^T = B^T A^T
+// (so that a skinny N takes the skinny-M tiles), split-K factor `split`
+void ws_run(Ctx &ctx, const GemmArgs &g, bool a_kc, bool b_nc, int shape, bool swap, int split) {
+    const WsShapeInfo &sh = kWsShapes[shape];
+    WsGemmArgs w;
+    const double *A = g.A, *B = g.B;
+    long long lda = g.lda, ldb = g.ldb, sA = g.strideA, sB = g.strideB;
+    w.M = g.M, w.N = g.N, w.K = g.K;
+    w.c_rs = g.ldc, w.c_cs = 1;
+    w.row_off = g.row_off, w.col_off = g.col_off;
+    if (swap) {
+        std::swap(A, B), std::swap(lda, ldb), std::swap(sA, sB);
+        std::swap(w.M, w.N), std::swap(w.c_rs, w.c_cs), std::swap(w.row_off, w.col_off);
+        const bool t = a_kc;
+        a_kc = !b_nc, b_nc = !t;
+    }
+    w.batch = g.batch, w.a_batched = (g.batch > 1 && sA != 0), w.b_batched = (g.batch > 1 && sB != 0);
+    w.alpha = g.alpha, w.beta = g.beta;
+    w.C = g.C, w.Cin = g.Cin, w.strideC = g.strideC, w.strideCin = g.Cin ? g.strideCin : g.strideC;
+    // A: [M][K] (K contiguous) -> {K, M}, box {16, BM};  [K][M] -> {M, K}, boxes {16, 16}
+    const CUtensorMap ta = a_kc ? ws_make_map(A, w.K, w.M, lda, g.batch, sA, sh.bm) : ws_make_map(A, w.M, w.K, lda, g.batch, sA, 16);
+    const CUtensorMap tb = b_nc ? ws_make_map(B, w.N, w.K, ldb, g.batch, sB, 16) : ws_make_map(B, w.K, w.N, ldb, g.batch, sB, sh.bn);
+    const int nkb = (w.K + WS_BK - 1) / WS_BK;
+    DBuf ws;
+    if (split > 1) {
+        const int per = (nkb + split - 1) / split;
+        split = (nkb + per - 1) / per;// no empty splits
+        w.kb_per_split = per;
+    }
+    if (split > 1) {
+        const long long tiles = (long long) ((w.M + sh.bm - 1) / sh.bm) * ((w.N + sh.bn - 1) / sh.bn);
+        ws = DBuf(ctx, (size_t) (tiles * g.batch * split * sh.bm * sh.bn));
+        w.ws = reinterpret_cast<double2 *>(ws.p);
+        w.counters = ctx.ws_counters;
+        w.k_splits = split;
+    }
+    ws_dispatch(ctx, shape, ta, tb, w, a_kc, b_nc);
+    ++ctx.ws_gemms;
+}
+
+struct WsChoice {
+    int shape;
+    bool swap;
+    int split;
+    double cost;
+};
+
+// estimated SM clocks: waves x per-CTA clocks (one CTA per SM, DMMA-bound at 64 FMA/clk/SM scaled by the tile's
+// fragment-load efficiency, or bound by streaming its operand bytes at the chip's ~3400 B/clk HBM rate shared by the
+// CTAs of a wave), plus the split-K partial traffic
+WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
+    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.65, 0.92};
+    WsChoice best{WS_64x64, false, 1, 1e300};
+    const int nkb = (g.K + WS_BK - 1) / WS_BK;
+    for (int swap = 0; swap < 2; ++swap) {
+        const long long M = swap ? g.N : g.M, N = swap ? g.M : g.N;
+        for (int t = 0; t < WS_SHAPE_COUNT; ++t) {
+            const WsShapeInfo &sh = kWsShapes[t];
+            if (t == WS_16x256 && M > 16) continue;
+            if (t == WS_48x256 && M > 48) continue;
+            if (swap && t != WS_16x256 && t != WS_48x256) continue;// the transposed problem only to reach the skinny-M tiles
+            const long long tiles = ((M + sh.bm - 1) / sh.bm) * ((N + sh.bn - 1) / sh.bn) * g.batch;
+            const long long slots = ctx.sm_count;
+            int cands[16], nc = 0;
+            for (int split = 1; split <= 512; split *= 2) cands[nc++] = split;
+            if (tiles < slots) cands[nc++] = (int) (slots / tiles), cands[nc++] = (int) ((2 * slots) / tiles);
+            for (int q = 0; q < nc; ++q) {
+                const int split = cands[q];
+                if (split > 1 && (nkb / split < 4 || tiles > ctx.ws_counters_cap)) continue;
+                const long long ctas = tiles * split;
+                const double waves = (double) ((ctas + slots - 1) / slots);
+                const double kb = (double) ((nkb + split - 1) / split);
+                const double mma = sh.bm * sh.bn * (kb + 4.0) / (4.0 * eff[t]);                  // clocks per CTA, tensor-bound
+                const double conc = (double) std::min<long long>(slots, ctas);
+                const double bytes = (sh.bm + sh.bn) * 16.0 * 8.0 * kb * conc / 3400.0 + 1500.0; // clocks per wave, HBM-bound (+ fill latency)
+                double cost = waves * std::max(mma, bytes);
+                if (split > 1) cost += 16.0 * sh.bm * sh.bn * (double) ctas / 6000.0 + 600.0;
+                if (cost < best.cost) best = WsChoice{t, swap != 0, split, cost};
+            }
+        }
+    }
+    return best;
+}
+
+}// namespace
 
 void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     QCP2_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "dgemm: negative extent");
@@ -104,6 +215,19 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
             return;
         }
     }
+    static const bool trace = getenv("QCP2_GEMM_TRACE") != nullptr;
+    if (ws_eligible(ctx, g)) {
+        WsChoice ch = ws_choose(ctx, g);
+        if (g.force_tile >= 0) ch.shape = g.force_tile & 7, ch.swap = (g.force_tile & 8) != 0, ch.split = 1;
+        if (g.force_split > 0) ch.split = g.force_split;
+        if (trace)
+            fprintf(stderr, "[qcp2 gemm] M %d N %d K %d batch %d  a_kc %d b_nc %d -> ws tile %dx%d%s split %d\n", g.M, g.N, g.K, g.batch,
+                    (int) a_kc, (int) b_nc, kWsShapes[ch.shape].bm, kWsShapes[ch.shape].bn, ch.swap ? " (transposed)" : "", ch.split);
+        ws_run(ctx, g, a_kc, b_nc, ch.shape, ch.swap, ch.split);
+        return;
+    }
+    QCP2_REQUIRE(g.row_off == nullptr, "dgemm: offset-table results need 16-byte aligned operands (warp-specialised kernel)");
+    ++ctx.legacy_gemms;
     const int vec = v2 ? 2 : 1;
     if (g.seg != nullptr) {
         QCP2_REQUIRE(a_kc && b_nc, "dgemm: segmented K needs [M][K] A and [K][N] B");
@@ -156,7 +280,6 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
         run.alpha = 1.0, run.beta = 0.0;
         run.k_splits = best_split, run.kb_per_split = (nkb + best_split - 1) / best_split;
     }
-    static const bool trace = getenv("QCP2_GEMM_TRACE") != nullptr;
     if (trace)
         fprintf(stderr, "[qcp2 gemm] M %d N %d K %d batch %d  a_kc %d b_nc %d -> tile %dx%d split %d\n", g.M, g.N, g.K, g.batch, (int) a_kc,
                 (int) b_nc, cand[best_t].bm, cand[best_t].bn, best_split);

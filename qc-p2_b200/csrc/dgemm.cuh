@@ -46,6 +46,11 @@ struct GemmArgs {
     // the caller owns every element of the M x ldc region behind C (padding columns included), so whole rows may
     // be exchanged between ranks by the row-sharded path
     bool c_owns_rows = false;
+    // optional result addressing through offset tables (device): &C[m][n] = C + row_off[m] + col_off[n]; the same
+    // addressing applies to Cin.  Only the warp-specialised kernel (dgemm_ws.cuh) implements it.
+    const long long *row_off = nullptr, *col_off = nullptr;
+    // tests / tuning: force a warp-specialised tile (WsShapeId, +8 = transposed problem) and a split-K factor
+    int force_tile = -1, force_split = 0;
     // SEG mode
     const SegDesc *seg = nullptr;
     int nseg = 0;

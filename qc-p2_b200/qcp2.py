@@ -46,6 +46,7 @@ def load_library():
         lib.qcp2_ccsd_t_count.restype = C.c_longlong
         lib.qcp2_ccsd_last_loop_seconds.restype = C.c_double
         lib.qcp2_sharded_gemms.restype = C.c_longlong
+        lib.qcp2_gemm_counts.restype = C.c_longlong
         _lib = lib
     return _lib
 
@@ -404,6 +405,23 @@ class Context:
         self.check(self.lib.qcp2_dgemm(self.h, int(transA), int(transB), M, N, K, C.c_double(alpha), _p(A),
                                        C.c_longlong(lda), _p(B), C.c_longlong(ldb), C.c_double(beta), _p(Cdev),
                                        C.c_longlong(ldc)))
+
+    def dgemm_ex(self, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, Cdev, ldc, batch=1, strideA=0, strideB=0,
+                 strideC=0, tile=-1, k_splits=0, reps=1):
+        """qcp2_dgemm_ex: device pointers, strided batch, forced tile / split-K of the warp-specialised TMA kernel;
+        returns the mean device seconds of one launch."""
+        secs = C.c_double()
+        self.check(self.lib.qcp2_dgemm_ex(self.h, int(transA), int(transB), M, N, K, C.c_double(alpha), _p(A), C.c_longlong(lda),
+                                          _p(B), C.c_longlong(ldb), C.c_double(beta), _p(Cdev), C.c_longlong(ldc), int(batch),
+                                          C.c_longlong(strideA), C.c_longlong(strideB), C.c_longlong(strideC), int(tile),
+                                          int(k_splits), int(reps), C.byref(secs)))
+        return secs.value
+
+    def gemm_counts(self):
+        """(products on the warp-specialised TMA kernel, products on the cp.async kernel) so far."""
+        legacy = C.c_longlong()
+        ws = int(self.lib.qcp2_gemm_counts(self.h, C.byref(legacy)))
+        return ws, int(legacy.value)
 
     def dgemm(self, transA, transB, alpha, A, B, beta, Cin):
         a, b, c = _arr(A), _arr(B), _arr(Cin).copy()

@@ -149,6 +149,7 @@ int qcp2_destroy(qcp2_ctx *ctx) {
         ctx->comm = nullptr;
     }
     if (ctx->c.ws_counters) cudaFree(ctx->c.ws_counters);
+    for (Ctx::OffsetTable &t : ctx->c.offset_tables) cudaFree(t.dev);
     if (ctx->c.pool) {
         cudaMemPoolTrimTo(ctx->c.pool, 0);
         cudaMemPoolDestroy(ctx->c.pool);

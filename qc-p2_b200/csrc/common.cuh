@@ -69,6 +69,13 @@ struct Ctx {
     unsigned int *ws_counters = nullptr;
     int ws_counters_cap = 0;
     long long ws_gemms = 0, legacy_gemms = 0;
+    // device offset tables of the GEMM's scatter epilogue, keyed by the contraction's signature (contract.cu); they
+    // live as long as the context, so a table made in an eager iteration is there when the same call is captured
+    struct OffsetTable {
+        std::string sig;
+        long long *dev;
+    };
+    std::vector<OffsetTable> offset_tables;
 
     // workspace pool owned by this context (created in qcp2_create, trimmed and destroyed in qcp2_destroy): freed
     // blocks stay cached here instead of in the device's default pool, so the library does not change the behaviour

@@ -47,7 +47,7 @@ struct Plan {
     double cost = 0.0;
 };
 
-Plan make_plan(const Spec &s, const std::string &M, const std::string &N, const std::string &K) {
+Plan make_plan(const Spec &s, const std::string &M, const std::string &N, const std::string &K, bool scatter_ok) {
     Plan p;
     p.M = M, p.N = N, p.K = K;
     if (s.a == M + K) p.a_direct = true, p.a_kc = true;
@@ -56,12 +56,13 @@ Plan make_plan(const Spec &s, const std::string &M, const std::string &N, const 
     else if (s.b == N + K) p.b_direct = true, p.b_nc = false;
     if (s.c == M + N) p.c_direct = true, p.c_swapped = false;
     else if (s.c == N + M) p.c_direct = true, p.c_swapped = true;
+    // a result written through offset tables costs a little (8-byte stores); without them a dense product + re-layout pass
     p.cost = (p.a_direct ? 0.0 : 2.0 * (double) total(s.a, s.ea)) + (p.b_direct ? 0.0 : 2.0 * (double) total(s.b, s.eb)) +
-             (p.c_direct ? 0.0 : 3.0 * (double) total(s.c, s.ec));
+             (p.c_direct ? 0.0 : (scatter_ok ? 0.25 : 3.0) * (double) total(s.c, s.ec));
     return p;
 }
 
-Plan best_plan(const Spec &s) {
+Plan best_plan(const Spec &s, bool scatter_ok) {
     std::string M, N, Ka, Kb;
     for (char l : s.c) {
         const bool ina = s.a.find(l) != std::string::npos, inb = s.b.find(l) != std::string::npos;
@@ -82,10 +83,24 @@ Plan best_plan(const Spec &s) {
     for (char l : Ka) QCP2_REQUIRE(ext_of(s.a, s.ea, l) == ext_of(s.b, s.eb, l), "contract: contracted extents differ");
     for (char l : M) QCP2_REQUIRE(ext_of(s.a, s.ea, l) == ext_of(s.c, s.ec, l), "contract: free extents differ (A)");
     for (char l : N) QCP2_REQUIRE(ext_of(s.b, s.eb, l) == ext_of(s.c, s.ec, l), "contract: free extents differ (B)");
-    Plan pa = make_plan(s, M, N, Ka);
-    if (Ka == Kb) return pa;
-    Plan pb = make_plan(s, M, N, Kb);
-    return pb.cost < pa.cost ? pb : pa;
+    // candidate orders of the free labels: as they appear in C, or as they appear in their own operand (then the
+    // operand is consumed in place and C is written through the GEMM's offset tables -- cheaper than re-laying a large
+    // operand out); contracted labels in A's or B's order
+    std::string Ma, Nb;
+    for (char l : s.a)
+        if (s.c.find(l) != std::string::npos) Ma.push_back(l);
+    for (char l : s.b)
+        if (s.c.find(l) != std::string::npos) Nb.push_back(l);
+    Plan best = make_plan(s, M, N, Ka, scatter_ok);
+    const std::string *Ms[2] = {&M, &Ma}, *Ns[2] = {&N, &Nb}, *Ks[2] = {&Ka, &Kb};
+    for (int im = 0; im < 2; ++im)
+        for (int in = 0; in < 2; ++in)
+            for (int ik = 0; ik < 2; ++ik) {
+                if ((im && Ma == M) || (in && Nb == N) || (ik && Kb == Ka)) continue;
+                Plan p = make_plan(s, *Ms[im], *Ns[in], *Ks[ik], scatter_ok);
+                if (p.cost < best.cost) best = p;
+            }
+    return best;
 }
 
 // re-lay `src` (labels `from`) out as a dense tensor with labels `to`
@@ -125,6 +140,42 @@ const double *operand_relayout(Ctx &ctx, DBuf &tmp, const double *src, long long
     return dst;
 }
 
+// Offset tables of a result whose index order interleaves the free labels of A and B:
+// &C[...] = C + row_off[m] + col_off[n], m / n the composite M / N indices in the plan's label order.
+// One device array [M + N], cached in the context under the call's signature.
+const long long *offset_tables(Ctx &ctx, const Spec &s, const Plan &p, long long M, long long N) {
+    std::string sig = s.c + "|" + p.M + "|" + p.N;
+    for (size_t k = 0; k < s.c.size(); ++k) sig += "," + std::to_string(s.ec[k]);
+    for (const Ctx::OffsetTable &t : ctx.offset_tables)
+        if (t.sig == sig) return t.dev;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(ctx.stream, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return nullptr;// cannot allocate / copy synchronously inside a capture
+    long long cstr[8], st = 1;
+    for (int k = (int) s.c.size() - 1; k >= 0; --k) cstr[k] = st, st *= s.ec[k];
+    std::vector<long long> tab((size_t) (M + N));
+    auto fill = [&](const std::string &labels, long long count, long long *out) {
+        for (long long lin = 0; lin < count; ++lin) {
+            long long rem = lin, off = 0;
+            for (int q = (int) labels.size() - 1; q >= 0; --q) {
+                const size_t pos = s.c.find(labels[q]);
+                const long long e = s.ec[pos];
+                off += (rem % e) * cstr[pos];
+                rem /= e;
+            }
+            out[lin] = off;
+        }
+    };
+    fill(p.M, M, tab.data());
+    fill(p.N, N, tab.data() + M);
+    long long *dev = nullptr;
+    QCP2_CUDA(cudaMalloc(&dev, tab.size() * sizeof(long long)));
+    QCP2_CUDA(cudaMemcpyAsync(dev, tab.data(), tab.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx.stream));
+    QCP2_CUDA(cudaStreamSynchronize(ctx.stream));// `tab` is pageable and goes out of scope
+    ctx.offset_tables.push_back(Ctx::OffsetTable{sig, dev});
+    return dev;
+}
+
 void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, double *C, const Spec &s,
          const Plan &p, int batch, long long sA, long long sB, long long sC, const double *cin) {
     const long long M = prod(p.M, s.c, s.ec), N = prod(p.N, s.c, s.ec), K = prod(p.K, s.a, s.ea);
@@ -149,8 +200,27 @@ void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, 
     double *Cg = C;
     long long sCg = sC;
     bool swapped = p.c_direct && p.c_swapped;
-    if (!p.c_direct) {
+    bool scatter = false;
+    if (!p.c_direct && !getenv("QCP2_NO_SCATTER_EPILOGUE") && !getenv("QCP2_NO_WS_GEMM")) {
+        // the result's index order interleaves the free labels of the two operands (cc.cpp:230, 246-249): the GEMM
+        // writes it in place through row / column offset tables instead of a dense product + re-layout pass
+        GemmArgs probe;
+        probe.A = Ag, probe.lda = a_kc ? K : M, probe.strideA = sAg, probe.B = Bg, probe.ldb = b_nc ? N : K, probe.strideB = sBg;
+        probe.K = (int) K, probe.batch = batch;
+        if (gemm_takes_tables(ctx, probe)) {
+            const long long *tab = offset_tables(ctx, s, p, M, N);
+            if (tab) {
+                scatter = true;
+                g.row_off = tab, g.col_off = tab + M;
+                g.beta = beta;
+                if (cin && beta != 0.0) g.Cin = cin, g.strideCin = sC;
+            }
+        }
+    }
+    if (scatter) {
+    } else if (!p.c_direct) {
         const long long n = total(s.c, s.ec);
+        if (cin && cin != C && beta != 0.0) axpby(ctx, C, cin, 1.0, 0.0, n * batch);// the result goes through a re-layout: seed C with cin
         tc = DBuf(ctx, (size_t) (n * batch));
         Cg = tc.p, sCg = n, g.beta = 0.0;
     } else {
@@ -170,7 +240,7 @@ void run(Ctx &ctx, double alpha, const double *A, const double *B, double beta, 
         g.C = Cg, g.ldc = M, g.strideC = sCg, g.ldcin = M;
         gemm(ctx, g, /*a_kc=*/!b_nc, /*b_nc=*/!a_kc);
     }
-    if (!p.c_direct) {
+    if (!p.c_direct && !scatter) {
         const std::string mn = p.M + p.N;
         long long emn[8];
         for (size_t k = 0; k < mn.size(); ++k) emn[k] = ext_of(s.c, s.ec, mn[k]);
@@ -191,7 +261,11 @@ void contract(Ctx &ctx, double alpha, const TView &A, const char *ia, const TVie
     for (int k = 0; k < B.rank; ++k) s.eb[k] = B.ext[k];
     for (int k = 0; k < C.rank; ++k) s.ec[k] = C.ext[k];
     if (C.size() == 0) return;
-    Plan p0 = best_plan(s);
+    // is the GEMM's offset-table epilogue available to this call?  (the planner prices interleaved results with it)
+    static const bool no_scatter = getenv("QCP2_NO_SCATTER_EPILOGUE") != nullptr || getenv("QCP2_NO_WS_GEMM") != nullptr;
+    const bool scatter_ok = !no_scatter && ctx.ws_counters != nullptr && !(ctx.shard) &&
+                            (reinterpret_cast<uintptr_t>(A.p) & 15) == 0 && (reinterpret_cast<uintptr_t>(B.p) & 15) == 0;
+    Plan p0 = best_plan(s, scatter_ok);
     // try peeling the leading label of C as a batch dimension
     bool peel = false;
     Spec sp = s;
@@ -215,19 +289,15 @@ void contract(Ctx &ctx, double alpha, const TView &A, const char *ia, const TVie
             }
             sC = total(sp.c, sp.ec);
             batch = (int) s.ec[0];
-            pp = best_plan(sp);
+            pp = best_plan(sp, scatter_ok);
             // cost of the peeled plan counts every batch member of the batched tensors
             const double scaled = (pp.a_direct ? 0.0 : 2.0 * (double) total(sp.a, sp.ea) * (sA ? batch : 1)) +
                                   (pp.b_direct ? 0.0 : 2.0 * (double) total(sp.b, sp.eb) * (sB ? batch : 1)) +
-                                  (pp.c_direct ? 0.0 : 3.0 * (double) total(sp.c, sp.ec) * batch);
+                                  (pp.c_direct ? 0.0 : (scatter_ok ? 0.25 : 3.0) * (double) total(sp.c, sp.ec) * batch);
             if (scaled < p0.cost) peel = true;
         }
     }
     const Plan &chosen = peel ? pp : p0;
-    if (cin && !chosen.c_direct) {// result goes through a re-layout: seed C with cin first
-        axpby(ctx, C.p, cin, 1.0, 0.0, C.size());
-        cin = nullptr;
-    }
     if (peel) run(ctx, alpha, A.p, B.p, beta, C.p, sp, pp, batch, sA, sB, sC, cin);
     else run(ctx, alpha, A.p, B.p, beta, C.p, s, p0, 1, 0, 0, 0, cin);
 }

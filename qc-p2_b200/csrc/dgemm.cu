@@ -52,6 +52,7 @@ void ws_dispatch(Ctx &ctx, int shape, const CUtensorMap &ta, const CUtensorMap &
         case WS_48x256: ws_launch_48x256(ctx, ta, tb, w, a_kc, b_nc); break;
         case WS_16x256: ws_launch_16x256(ctx, ta, tb, w, a_kc, b_nc); break;
         case WS_64x64: ws_launch_64x64(ctx, ta, tb, w, a_kc, b_nc); break;
+        case WS_16x192: ws_launch_16x192(ctx, ta, tb, w, a_kc, b_nc); break;
         default: ws_launch_112x128(ctx, ta, tb, w, a_kc, b_nc); break;
     }
 }
@@ -107,16 +108,16 @@ struct WsChoice {
 // fragment-load efficiency, or bound by streaming its operand bytes at the chip's ~3400 B/clk HBM rate shared by the
 // CTAs of a wave), plus the split-K partial traffic
 WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
-    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.65, 0.92};
+    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.65, 0.92, 0.68};
     WsChoice best{WS_64x64, false, 1, 1e300};
     const int nkb = (g.K + WS_BK - 1) / WS_BK;
     for (int swap = 0; swap < 2; ++swap) {
         const long long M = swap ? g.N : g.M, N = swap ? g.M : g.N;
         for (int t = 0; t < WS_SHAPE_COUNT; ++t) {
             const WsShapeInfo &sh = kWsShapes[t];
-            if (t == WS_16x256 && M > 16) continue;
+            if ((t == WS_16x256 || t == WS_16x192) && M > 16) continue;
             if (t == WS_48x256 && M > 48) continue;
-            if (swap && t != WS_16x256 && t != WS_48x256) continue;// the transposed problem only to reach the skinny-M tiles
+            if (swap && t != WS_16x256 && t != WS_16x192 && t != WS_48x256) continue;// the transposed problem only to reach the skinny-M tiles
             const long long tiles = ((M + sh.bm - 1) / sh.bm) * ((N + sh.bn - 1) / sh.bn) * g.batch;
             const long long slots = ctx.sm_count;
             int cands[16], nc = 0;
@@ -130,9 +131,12 @@ WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
                 const double kb = (double) ((nkb + split - 1) / split);
                 const double mma = sh.bm * sh.bn * (kb + 4.0) / (4.0 * eff[t]);                  // clocks per CTA, tensor-bound
                 const double conc = (double) std::min<long long>(slots, ctas);
-                const double bytes = (sh.bm + sh.bn) * 16.0 * 8.0 * kb * conc / 3400.0 + 1500.0; // clocks per wave, HBM-bound (+ fill latency)
+                // rows past the M / N edge are zero-filled by the copy engine without memory traffic
+                const double rows = (double) std::min<long long>(sh.bm, M) + (double) std::min<long long>(sh.bn, N);
+                const double bytes = rows * 16.0 * 8.0 * kb * conc / 3400.0 + 1500.0;            // clocks per wave, HBM-bound (+ fill latency)
                 double cost = waves * std::max(mma, bytes);
-                if (split > 1) cost += 16.0 * sh.bm * sh.bn * (double) ctas / 6000.0 + 600.0;
+                // split-K: every CTA writes its partial tile; the last CTA of a tile reads all of them back (~150 B/clk)
+                if (split > 1) cost += 8.0 * sh.bm * sh.bn * (double) ctas / 6000.0 + 8.0 * sh.bm * sh.bn * split / 150.0 + 600.0;
                 if (cost < best.cost) best = WsChoice{t, swap != 0, split, cost};
             }
         }
@@ -141,6 +145,11 @@ WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
 }
 
 }// namespace
+
+bool gemm_takes_tables(const Ctx &ctx, const GemmArgs &g) {
+    if (ctx.shard && ctx.shard->nranks > 1) return false;// the row-sharded path assembles dense row-major results
+    return ws_eligible(ctx, g);
+}
 
 void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     QCP2_REQUIRE(g.M >= 0 && g.N >= 0 && g.K >= 0, "dgemm: negative extent");
@@ -157,7 +166,7 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     // workspace, ONE in-place ncclAllGather assembles the product on every rank, the first M rows are copied to C.
     // Columns (N > M, beta = 0): the same on the transposed problem C^T = B^T A^T, followed by a transposing copy.
     // Every rank takes the same decision (same shapes, same threshold), so the collectives match up.
-    if (ctx.shard && ctx.shard->nranks > 1 && g.seg == nullptr && g.batch == 1 && g.k_splits == 1 &&
+    if (ctx.shard && ctx.shard->nranks > 1 && g.seg == nullptr && g.batch == 1 && g.k_splits == 1 && g.row_off == nullptr &&
         (g.ldc == g.N || g.c_owns_rows) && 2.0 * g.M * g.N * g.K >= ctx.shard_min_flops) {
         Comm *cm = ctx.shard;
         const int W = cm->nranks;

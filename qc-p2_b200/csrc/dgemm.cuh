@@ -284,5 +284,7 @@ void launch_dgemm_t(Ctx &ctx, const GemmArgs &g, int vec, bool seg);
 
 // dgemm.cu: alignment analysis + tile choice
 void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc);
+// true if gemm() will run g on the warp-specialised TMA kernel (the only one with offset-table results)
+bool gemm_takes_tables(const Ctx &ctx, const GemmArgs &g);
 
 }// namespace qcp2

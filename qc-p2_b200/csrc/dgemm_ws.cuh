@@ -271,8 +271,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
             for (int j = 0; j < FN; ++j) {
                 double s0 = 0.0, s1 = 0.0;
-                for (int q = 0; q < g.k_splits; ++q) {// split order: the sum does not depend on which CTA arrived last
-                    const double2 p = __ldcg(all + ((long long) q * (FM * FN) + i * FN + j) * 256);
+                // split order: the sum does not depend on which CTA arrived last.  Eight independent loads are in
+                // flight before the first add, so the walk over the partials is bandwidth- rather than latency-bound.
+                const double2 *src = all + (i * FN + j) * 256;
+                int q = 0;
+                for (; q + 8 <= g.k_splits; q += 8) {
+                    double2 p[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) p[u] = __ldcg(src + (long long) (q + u) * (FM * FN * 256));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s0 += p[u].x, s1 += p[u].y;
+                }
+                for (; q < g.k_splits; ++q) {
+                    const double2 p = __ldcg(src + (long long) q * (FM * FN * 256));
                     s0 += p.x, s1 += p.y;
                 }
                 acc[i][j][0] = s0, acc[i][j][1] = s1;
@@ -292,27 +303,45 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         const int row = m0 + (i * NWM + w_m) * 8 + g8;
         if (row >= g.M) continue;
         const long long roff = tables ? g.row_off[row] : (long long) row * g.c_rs;
+        // all beta-term loads of this fragment row are issued before its first store (C and Cin may alias, so the
+        // compiler cannot hoist them itself): one round trip per row instead of one per 8x8 fragment
+        double old0[FN], old1[FN];
+        long long o0[FN], o1[FN];
+#pragma unroll
+        for (int j = 0; j < FN; ++j) {
+            const int col = n0 + (j * NWN + w_n) * 8 + 2 * t4;
+            old0[j] = old1[j] = 0.0;
+            o0[j] = o1[j] = 0;
+            if (col >= g.N) continue;
+            if (vec_ok) {
+                o0[j] = roff + col;
+                if (use_beta) {
+                    if (col + 1 < g.N) {
+                        const double2 old = *reinterpret_cast<const double2 *>(Cin + o0[j]);
+                        old0[j] = old.x, old1[j] = old.y;
+                    } else {
+                        old0[j] = Cin[o0[j]];
+                    }
+                }
+            } else {
+                o0[j] = roff + (tables ? g.col_off[col] : (long long) col * g.c_cs);
+                if (col + 1 < g.N) o1[j] = roff + (tables ? g.col_off[col + 1] : (long long) (col + 1) * g.c_cs);
+                if (use_beta) {
+                    old0[j] = Cin[o0[j]];
+                    if (col + 1 < g.N) old1[j] = Cin[o1[j]];
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < FN; ++j) {
             const int col = n0 + (j * NWN + w_n) * 8 + 2 * t4;
             if (col >= g.N) continue;
-            double v0 = g.alpha * acc[i][j][0], v1 = g.alpha * acc[i][j][1];
+            const double v0 = g.alpha * acc[i][j][0] + g.beta * old0[j], v1 = g.alpha * acc[i][j][1] + g.beta * old1[j];
             if (vec_ok && col + 1 < g.N) {
-                const long long o = roff + col;
-                if (use_beta) {
-                    const double2 old = *reinterpret_cast<const double2 *>(Cin + o);
-                    v0 += g.beta * old.x, v1 += g.beta * old.y;
-                }
-                *reinterpret_cast<double2 *>(C + o) = make_double2(v0, v1);
+                *reinterpret_cast<double2 *>(C + o0[j]) = make_double2(v0, v1);
             } else {
-                const long long o0 = roff + (tables ? g.col_off[col] : (long long) col * g.c_cs);
-                if (use_beta) v0 += g.beta * Cin[o0];
-                C[o0] = v0;
-                if (col + 1 < g.N) {
-                    const long long o1 = roff + (tables ? g.col_off[col + 1] : (long long) (col + 1) * g.c_cs);
-                    if (use_beta) v1 += g.beta * Cin[o1];
-                    C[o1] = v1;
-                }
+                C[o0[j]] = v0;
+                if (col + 1 < g.N) C[vec_ok ? o0[j] + 1 : o1[j]] = v1;
             }
         }
     }
@@ -349,12 +378,13 @@ void ws_launch_shape(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, c
 }
 
 // tile shapes (one translation unit each, dgemm_ws_*.cu)
-enum WsShapeId { WS_80x256 = 0, WS_48x256, WS_16x256, WS_64x64, WS_112x128, WS_SHAPE_COUNT };
+enum WsShapeId { WS_80x256 = 0, WS_48x256, WS_16x256, WS_64x64, WS_112x128, WS_16x192, WS_SHAPE_COUNT };
 using WsS80 = WsShape<2, 4, 5, 8>;  // the (T) tile: 40x64 per warp, 13 fragment loads per 40 DMMA
 using WsS48 = WsShape<1, 8, 6, 4>;  // M <= 48 (packed ladder, M = o(o-1)/2 = 45): 48x32 per warp
 using WsS16 = WsShape<1, 8, 2, 4>;  // M <= 16: HBM-bound streaming of the other operand
 using WsS64 = WsShape<2, 4, 4, 2>;  // small products / one-wave split-K
 using WsS112 = WsShape<2, 4, 7, 4>; // M = o^2 = 100
+using WsS16N = WsShape<1, 8, 2, 3>; // M <= 16, N = v = 162 and the like: 16x192 wastes less of the tensor pipe than 16x256
 struct WsShapeInfo {
     int bm, bn, stages;
 };
@@ -364,5 +394,6 @@ void ws_launch_48x256(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, 
 void ws_launch_16x256(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
 void ws_launch_64x64(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
 void ws_launch_112x128(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
+void ws_launch_16x192(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
 
 }// namespace qcp2

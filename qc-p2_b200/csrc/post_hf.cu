@@ -180,8 +180,7 @@ void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
 // with tau = tau(Ts, Td) and tau_old / t_old the amplitudes the intermediates were built from
 // (Ts_old; cc.cpp:442-446 feeds make_T2 the NEW T1 but OLD intermediates).
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
-                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new, const double *Ts_old,
-                 const LadderPack *pack) {
+                 const double *fvv, const double *D_ijab, int o, int v, double *T2_new, const double *Ts_old) {
     const long long O = o, V = v, o2v2 = O * O * V * V;
     const TView ts(Ts, {O, V}), td(Td, {O, O, V, V});
     const TView Fae(X.p[X_FAE], {V, V}), Fmi(X.p[X_FMI], {O, O}), Fme(X.p[X_FME], {O, V});
@@ -234,30 +233,7 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
         DBuf tau_old(ctx, (size_t) o2v2), y(ctx, (size_t) (O * O * O * O)), z(ctx, (size_t) (O * O * V * O));
         make_tau(ctx, Ts_old, Td, o, v, false, tau_old);
         const TView vtauo(tau_old.p, {O, O, V, V}), Y(y.p, {O, O, O, O}), Z(z.p, {O, O, V, O});
-        bool packed = false;
-        if (pack && pack->vvvvP && pack->npo > 0 && pack->npv > 0 && pack->tau_antisymmetric >= 0) {
-            packed = pack->tau_antisymmetric != 0;
-        } else if (pack && pack->vvvvP && pack->npo > 0 && pack->npv > 0) {// tau must be antisymmetric for the e<f / i<j restriction
-            double d0, d1, m0, m1;
-            antisymmetry_defect(ctx, tau, O, O, V, V, 0, &d0, &m0);
-            antisymmetry_defect(ctx, tau, O, O, V, V, 1, &d1, &m1);
-            packed = d0 <= 1e-10 * m0 && d1 <= 1e-10 * m1;
-        }
-        if (packed) {
-            // sum over e<f only (x2 cancels the 1/2), rows i<j, columns a<b: 1/8 of the flops of the dense product
-            const long long ld = pack->ld;// even: 16-byte aligned rows
-            DBuf tauP(ctx, (size_t) (pack->npo * ld)), lp(ctx, (size_t) (pack->npo * ld));
-            pack_pairs(ctx, tau, o, v, pack->pairs_o, pack->npo, tauP, ld);
-            GemmArgs g;
-            g.M = pack->npo, g.N = pack->npv, g.K = pack->npv;
-            g.A = tauP, g.lda = ld;         // [M][K]
-            g.B = pack->vvvvP, g.ldb = ld;  // [N][K]
-            g.C = lp, g.ldc = ld, g.c_owns_rows = true;
-            gemm(ctx, g, true, false);
-            unpack_add_pairs(ctx, lp, ld, o, v, r);
-        } else {
-            contract(ctx, 0.5, vtau, "ijef", vvvv, "abef", 1.0, R, "ijab");// 1/2 tau <ab||ef>         (cc.cpp:240 in :348)
-        }
+        contract(ctx, 0.5, vtau, "ijef", vvvv, "abef", 1.0, R, "ijab");    // 1/2 tau <ab||ef>         (cc.cpp:240 in :348)
         contract(ctx, 1.0, vtau, "ijef", oovv, "mnef", 0.0, Y, "ijmn");   // 1/8 tau <mn||ef> tau_old  (cc.cpp:239 in :348)
         contract(ctx, 0.125, Y, "ijmn", vtauo, "mnab", 1.0, R, "ijab");
         contract(ctx, 1.0, vtau, "ijef", vovv, "amef", 0.0, Z, "ijam");   // -1/2 P(ab) tau <am||ef> t (cc.cpp:237-238 in :348)
@@ -317,35 +293,14 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         xbuf[k] = DBuf(ctx, (size_t) inter_block_size(k, o, v)), X.p[k] = xbuf[k].p;
     }
     DBuf t1n(ctx, (size_t) (O * V)), t2n(ctx, (size_t) o2v2), e_dev(ctx, 1);
-    // packed particle-particle ladder operands, only when <vv||vv> has both antisymmetries (RHF-type inputs;
-    // the as-written UHF integrals lose the ket antisymmetry, SURVEY.md Q5, and take the dense product)
-    LadderPack pack;
-    DBuf vvvvP;
+    // Inputs with the permutational symmetries of real (RHF-type) integrals take the pair-packed / factorised
+    // iteration of ccsd_sym.cu; the check runs once, on the device (the iteration preserves the antisymmetry of T2:
+    // every term enters with its P(ij) / P(ab) partner).  Anything else -- the as-written UHF integrals lose the ket
+    // antisymmetry, SURVEY.md Q5 -- keeps the dense term list below.
     Trace tr(ctx, "ccsd_dev");
-    int *pairs_dev = nullptr;
-    if (o >= 2 && v >= 2 && !getenv("QCP2_CCSD_DENSE_LADDER")) {
-        double d0, d1, m0, m1;
-        antisymmetry_defect(ctx, I.p[I_VVVV], V, V, V, V, 0, &d0, &m0);
-        tr.mark("antisymmetry of <vv||vv> in (a,b)");
-        antisymmetry_defect(ctx, I.p[I_VVVV], V, V, V, V, 1, &d1, &m1);
-        tr.mark("antisymmetry of <vv||vv> in (e,f)");
-        if (d0 <= 1e-10 * m0 && d1 <= 1e-10 * m1) {
-            std::vector<int> po, pv;
-            for (int i = 0; i < o; ++i)
-                for (int j = i + 1; j < o; ++j) po.push_back(i), po.push_back(j);
-            for (int a = 0; a < v; ++a)
-                for (int b = a + 1; b < v; ++b) pv.push_back(a), pv.push_back(b);
-            QCP2_CUDA(cudaMalloc(&pairs_dev, (po.size() + pv.size()) * sizeof(int)));
-            QCP2_CUDA(cudaMemcpy(pairs_dev, po.data(), po.size() * sizeof(int), cudaMemcpyHostToDevice));
-            QCP2_CUDA(cudaMemcpy(pairs_dev + po.size(), pv.data(), pv.size() * sizeof(int), cudaMemcpyHostToDevice));
-            pack.npo = (int) (po.size() / 2), pack.npv = (int) (pv.size() / 2);
-            pack.ld = ((long long) pack.npv + 1) & ~1LL;
-            vvvvP = DBuf(ctx, (size_t) (pack.npv * pack.ld));
-            pack_pairs(ctx, I.p[I_VVVV], v, v, pairs_dev + po.size(), pack.npv, vvvvP, pack.ld);
-            pack.vvvvP = vvvvP.p, pack.pairs_o = pairs_dev;
-            tr.mark("pack <vv||vv> to a<b, e<f");
-        }
-    }
+    SymPack sp;
+    const bool sym = sym_setup(ctx, I, T2_guess, o, v, sp);
+    tr.mark(sym ? "symmetric formulation: checks + packing" : "dense formulation (symmetry checks)");
     // the integral blocks are constant for the whole loop: their operand re-layouts are made once
     PermCache perm_cache;
     for (int k = 0; k < I_COUNT; ++k)
@@ -360,7 +315,6 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
         }
     } cache_guard(ctx, perm_cache);
     if (getenv("QCP2_CCSD_NO_PERM_CACHE")) ctx.perm_cache = nullptr;
-    unsigned long long *chk_dev = static_cast<unsigned long long *>(ctx.alloc_bytes(32));
     fill_zero(ctx, T1, O * V);                                                             // :417-419
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
     cudaEvent_t ev0, ev1;
@@ -373,34 +327,23 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     // on it is replayed as a CUDA graph (stream capture, incl. the stream-ordered workspace allocations), which
     // removes the launch gaps that dominate small molecules.  QCP2_CCSD_NO_GRAPH=1 keeps the eager path.
     auto body = [&]() {
-        update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);                  // :442
-        make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);                 // :445
-        make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1, &pack);          // :446: new T1, old T2, old X
+        if (sym) {
+            ccsd_sym_iteration(ctx, I, foo, fov, fvv, o, v, sp, T1, T2, t1n, t2n);         // :442-446
+        } else {
+            update_intermediates_dev(ctx, T1, T2, I, foo, fov, fvv, o, v, X);              // :442
+            make_T1_dev(ctx, T1, T2, I, X, foo, fov, fvv, nullptr, o, v, t1n);             // :445
+            make_T2_dev(ctx, t1n, T2, I, X, foo, fvv, nullptr, o, v, t2n, T1);             // :446: new T1, old T2, old X
+        }
         QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     };
     bool use_graph = getenv("QCP2_CCSD_NO_GRAPH") == nullptr && ctx.shard == nullptr;// (NCCL calls stay outside graphs)
     cudaGraphExec_t graph_exec = nullptr;
-    int graph_flag = -2;
     long long graph_launches = 0;
     for (; it < maxiter; ++it) {
         ccsd_energy(ctx, T1, T2, I.p[I_OOVV], fov, o, v, e_dev);                           // :432
-        // the packed ladder needs antisymmetric doubles (tau = T2 + an antisymmetric product of singles); the check
-        // rides on the iteration's one host synchronisation instead of stalling the stream inside make_T2
-        unsigned long long chk[4] = {0, 0, 0, 0};
-        if (pack.vvvvP) {
-            QCP2_CUDA(cudaMemsetAsync(chk_dev, 0, 32, ctx.stream));
-            antisymmetry_defect_async(ctx, T2, O, O, V, V, 0, chk_dev);
-            antisymmetry_defect_async(ctx, T2, O, O, V, V, 1, chk_dev + 2);
-            QCP2_CUDA(cudaMemcpyAsync(chk, chk_dev, 32, cudaMemcpyDeviceToHost, ctx.stream));
-        }
         QCP2_CUDA(cudaMemcpyAsync(&e, e_dev.p, 8, cudaMemcpyDeviceToHost, ctx.stream));
         ctx.sync();
-        if (pack.vvvvP) {
-            double dm[4];
-            memcpy(dm, chk, 32);
-            pack.tau_antisymmetric = (dm[0] <= 1e-10 * dm[1] && dm[2] <= 1e-10 * dm[3]) ? 1 : 0;
-        }
         const double de = e - e_last;
         e_last = e;
         if (e_hist_host) e_hist_host[it] = e;
@@ -409,8 +352,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
             body();
             continue;
         }
-        if (!graph_exec || graph_flag != pack.tau_antisymmetric) {
-            if (graph_exec) cudaGraphExecDestroy(graph_exec), graph_exec = nullptr;
+        if (!graph_exec) {
             const long long l0 = ctx.launches;
             cudaGraph_t graph = nullptr;
             bool ok = cudaStreamBeginCapture(ctx.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
@@ -435,7 +377,6 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
             }
             graph_launches = ctx.launches - l0;
             ctx.launches = l0;
-            graph_flag = pack.tau_antisymmetric;
         }
         QCP2_CUDA(cudaGraphLaunch(graph_exec, ctx.stream));
         ctx.launches += graph_launches;
@@ -452,8 +393,6 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     ctx.ccsd_loop_seconds = ms * 1e-3;
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
-    if (pairs_dev) cudaFree(pairs_dev);
-    ctx.free(chk_dev);
     *e_host = e;
     if (iters_host) *iters_host = it;
 }

@@ -9,15 +9,14 @@ enum IntBlock { I_OOOO, I_OVOO, I_OOVO, I_OOOV, I_OVOV, I_OVVO, I_OOVV, I_VOVV, 
 extern const char *const kIntNames[I_COUNT];
 enum InterBlock { X_FAE, X_FMI, X_FME, X_WMNIJ, X_WMBEJ, X_WABEF, X_COUNT };
 
-// b<c / i<j packed operands of the particle-particle ladder (valid for antisymmetric integrals only)
-struct LadderPack {
-    const double *vvvvP = nullptr;// [v(v-1)/2][v(v-1)/2]
-    const int *pairs_o = nullptr; // device, 2 ints per i<j pair
+// Pair-packed constants of the symmetric CCSD iteration (ccsd_sym.cu); built once per solve by sym_setup()
+struct SymPack {
+    DBuf pairs_buf, ladB, oovvA, tauoP, ovvo_mebj;
+    const int *pairs_o = nullptr;   // i<j pairs (2 ints each)
+    const int *pairs_all = nullptr; // all (i,n) pairs
     int npo = 0, npv = 0;
-    long long ld = 0;            // row stride of the packed operands (npv rounded up to even)
-    // >= 0: the caller already knows whether the doubles amplitudes (hence tau) are antisymmetric in (i,j) and
-    // (a,b) (ccsd_dev reads the check back together with the iteration's energy); < 0: check tau here
-    int tau_antisymmetric = -1;
+    long long ld = 0, ldo = 0;      // row strides of [..][a<b] and [..][i<j] matrices (even)
+    long long offZ = 0, offY = 0, ntot = 0, ldl = 0;// row segments of ladB = column segments of tauP . ladB^T
 };
 
 struct IntsDev {
@@ -40,7 +39,11 @@ void make_T1_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
                  const double *fov, const double *fvv, const double *D_ia, int o, int v, double *T1_new);
 void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I, const InterDev &X, const double *foo,
                  const double *fvv, const double *D_ijab, int o, int v, double *T2_new,
-                 const double *Ts_old = nullptr, const struct LadderPack *pack = nullptr);
+                 const double *Ts_old = nullptr);
+// ccsd_sym.cu: true if every permutational symmetry the packed formulation relies on holds (checked on the device)
+bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp);
+void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv, int o, int v,
+                        const SymPack &sp, const double *T1, const double *T2, double *T1n, double *T2n);
 void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,
               const double *T2_guess, int o, int v, int maxiter, double conv, double *T1, double *T2, double *e_host,
               int *iters_host, double *e_hist_host);

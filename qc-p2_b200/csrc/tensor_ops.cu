@@ -454,7 +454,7 @@ __global__ void wmbej_amp_kernel(const double *__restrict__ ts, const double *__
     const double *src = td + ((size_t) j * o + n) * v * v;
     for (int r = ty; r < 32; r += 8) {
         const int f = f0 + r, b = b0 + tx;
-        if (f < v && b < v) tile[r][tx] = -0.5 * src[(size_t) f * v + b] - ts[j * v + f] * ts[n * v + b];
+        if (f < v && b < v) tile[r][tx] = -0.5 * src[(size_t) f * v + b] - (ts ? ts[j * v + f] * ts[n * v + b] : 0.0);
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
@@ -645,9 +645,159 @@ __global__ void pack_pairs_kernel(const double *__restrict__ src, int d01, int d
 }
 void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld) {
     if (n01 <= 0 || d23 < 2) return;
-    const unsigned ny = n01 >= 4 * ctx.sm_count ? 1u : (unsigned) std::min(d23 - 1, (4 * ctx.sm_count + n01 - 1) / n01);
-    pack_pairs_kernel<<<dim3((unsigned) n01, ny), kBlock, 0, ctx.stream>>>(src, d01, d23, pairs01, dst, ld);
+    const unsigned ny = n01 >= 8 * ctx.sm_count ? 1u : (unsigned) std::min(d23 - 1, (8 * ctx.sm_count + n01 - 1) / n01);
+    pack_pairs_kernel<<<dim3((unsigned) n01, ny), d23 >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(src, d01, d23, pairs01, dst, ld);
     ctx.launched("pack_pairs");
+}
+
+// dst[p(i<j)][q(a<b)] = Td[i,j,a,b] + t_ia t_jb - t_ib t_ja (Stanton eq. 9 on the packed pairs only)
+__global__ void tau_pack_kernel(const double *__restrict__ ts, const double *__restrict__ td, int o, int v,
+                                const int *__restrict__ pairs_o, double *__restrict__ dst, long long ld, double f) {
+    const int i = pairs_o[2 * blockIdx.x], j = pairs_o[2 * blockIdx.x + 1];
+    const double *s = td + ((size_t) i * o + j) * v * v;
+    const double *ti = ts + (size_t) i * v, *tj = ts + (size_t) j * v;
+    double *d = dst + (size_t) blockIdx.x * (size_t) ld;
+    for (int a = blockIdx.y; a + 1 < v; a += gridDim.y) {
+        const size_t q0 = (size_t) a * v - (size_t) a * (a + 1) / 2 - (a + 1);
+        const double tia = f * ti[a], tja = f * tj[a];
+        for (int b = a + 1 + threadIdx.x; b < v; b += blockDim.x) d[q0 + b] = s[(size_t) a * v + b] + tia * tj[b] - ti[b] * tja;
+    }
+}
+void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,
+              bool bar) {
+    if (npo <= 0 || v < 2) return;
+    const unsigned ny = (unsigned) std::min(v - 1, (8 * ctx.sm_count + npo - 1) / npo);
+    tau_pack_kernel<<<dim3((unsigned) npo, ny), v >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(Ts, Td, o, v, pairs_o, dst, ld,
+                                                                                             bar ? 0.5 : 1.0);
+    ctx.launched("tau_pack");
+}
+
+// F[m][i] += sum_n G[(i,n)][(m,n)]   (G is [o*o][ldg]: the n = n' trace of an all-pairs product, cc.cpp:209)
+__global__ void pair_trace_add_kernel(const double *__restrict__ G, long long ldg, int o, double *__restrict__ F) {
+    const int n2 = o * o;
+    GRID_STRIDE(lin, (long long) n2) {
+        const int m = (int) (lin / o), i = (int) (lin % o);
+        double s = 0.0;
+        for (int n = 0; n < o; ++n) s += G[(long long) (i * o + n) * ldg + (m * o + n)];
+        F[lin] += s;
+    }
+}
+void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, double *F) {
+    if (o <= 0) return;
+    pair_trace_add_kernel<<<grid_for((long long) o * o, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(G, ldg, o, F);
+    ctx.launched("pair_trace_add");
+}
+
+// The last step of the fused T2 equation (cc.cpp:312-383 assembled in one pass):
+//   r = <ij||ab> + P(ab) Uab + P(ij) Uij + P(ij)P(ab) Rt[i,a,b,j] + s(ij) s(ab) LP[i<j][a<b];   T2_new = r / D_ijab
+__global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double *__restrict__ Uab, const double *__restrict__ Uij,
+                                   const double *__restrict__ Rt, const double *__restrict__ LP, long long ldl,
+                                   const double *__restrict__ foo, const double *__restrict__ fvv, const double *__restrict__ D,
+                                   int o, int v, double *__restrict__ out) {
+    const long long n = (long long) o * o * v * v, vv = (long long) v * v;
+    GRID_STRIDE(lin, n) {
+        long long q = lin;
+        const int b = (int) (q % v);
+        q /= v;
+        const int a = (int) (q % v);
+        q /= v;
+        const int j = (int) (q % o);
+        const int i = (int) (q / o);
+        const long long ijba = ((long long) i * o + j) * vv + (long long) b * v + a;
+        const long long jiab = ((long long) j * o + i) * vv + (long long) a * v + b;
+        auto at = [&](int x, int c, int d, int y) { return Rt[(((long long) x * v + c) * v + d) * o + y]; };
+        double x = oovv[lin] + (Uab[lin] - Uab[ijba]) + (Uij[lin] - Uij[jiab]);
+        x += at(i, a, b, j) - at(j, a, b, i) - at(i, b, a, j) + at(j, b, a, i);
+        if (i != j && a != b) {
+            int i0 = i, j0 = j, a0 = a, b0 = b;
+            double sign = 1.0;
+            if (i0 > j0) {
+                const int t = i0;
+                i0 = j0, j0 = t, sign = -sign;
+            }
+            if (a0 > b0) {
+                const int t = a0;
+                a0 = b0, b0 = t, sign = -sign;
+            }
+            const long long pij = (long long) i0 * o - (long long) i0 * (i0 + 1) / 2 + (j0 - i0 - 1);
+            const long long pab = (long long) a0 * v - (long long) a0 * (a0 + 1) / 2 + (b0 - a0 - 1);
+            x += sign * LP[pij * ldl + pab];
+        }
+        const double d = D ? D[lin]
+                           : foo[(long long) i * o + i] + foo[(long long) j * o + j] - fvv[(long long) a * v + a] - fvv[(long long) b * v + b];
+        out[lin] = x / d;
+    }
+}
+void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *LP, long long ldl,
+                 const double *foo, const double *fvv, const double *D, int o, int v, double *out) {
+    const long long n = (long long) o * o * v * v;
+    if (n == 0) return;
+    finalize_t2_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(oovv, Uab, Uij, Rt, LP, ldl, foo, fvv, D, o, v, out);
+    ctx.launched("finalize_t2");
+}
+
+// WP[p(i<j)][q(m<n)] = W[m,n,i,j]  (W_mnij as the left factor of sum_{m<n} W_mnij tau_mnab on packed pairs)
+__global__ void wmnij_pack_kernel(const double *__restrict__ W, int o, const int *__restrict__ pairs_o, int npo,
+                                  double *__restrict__ dst, long long ld) {
+    const long long n = (long long) npo * npo;
+    GRID_STRIDE(lin, n) {
+        const int p = (int) (lin / npo), q = (int) (lin % npo);
+        const int i = pairs_o[2 * p], j = pairs_o[2 * p + 1], m = pairs_o[2 * q], nn = pairs_o[2 * q + 1];
+        dst[(long long) p * ld + q] = W[(((long long) m * o + nn) * o + i) * o + j];
+    }
+}
+void wmnij_pack(Ctx &ctx, const double *W, int o, const int *pairs_o, int npo, double *dst, long long ld) {
+    if (npo <= 0) return;
+    wmnij_pack_kernel<<<grid_for((long long) npo * npo, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(W, o, pairs_o, npo, dst, ld);
+    ctx.launched("wmnij_pack");
+}
+
+// W[m,n,i,j] += s(mn) s(ij) alpha WP[p(i<j)][q(m<n)]: the packed 1/4 tau_ijef <mn||ef> term of W_mnij (cc.cpp:231)
+__global__ void wmnij_unpack_add_kernel(const double *__restrict__ WP, long long ld, int o, double alpha, double *__restrict__ W) {
+    const long long n = (long long) o * o * o * o;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        int j = (int) (r % o);
+        r /= o;
+        int i = (int) (r % o);
+        r /= o;
+        int nn = (int) (r % o);
+        int m = (int) (r / o);
+        if (i == j || m == nn) continue;
+        double sign = alpha;
+        if (i > j) {
+            const int t = i;
+            i = j, j = t, sign = -sign;
+        }
+        if (m > nn) {
+            const int t = m;
+            m = nn, nn = t, sign = -sign;
+        }
+        const long long pij = (long long) i * o - (long long) i * (i + 1) / 2 + (j - i - 1);
+        const long long pmn = (long long) m * o - (long long) m * (m + 1) / 2 + (nn - m - 1);
+        W[lin] += sign * WP[pij * ld + pmn];
+    }
+}
+void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, double alpha, double *W) {
+    if (o < 2) return;
+    wmnij_unpack_add_kernel<<<grid_for((long long) o * o * o * o, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(WP, ld, o, alpha, W);
+    ctx.launched("wmnij_unpack_add");
+}
+
+// LP[p][q(a<b)] -= X[p][a][b] - X[p][b][a]   (X is [npo][v][v]: the P(ab) of the tau.<am||ef>.t term on packed pairs)
+__global__ void packed_antisym_sub_kernel(const double *__restrict__ X, int v, double *__restrict__ LP, long long ld) {
+    const double *x = X + (size_t) blockIdx.x * v * v;
+    double *d = LP + (size_t) blockIdx.x * (size_t) ld;
+    for (int a = blockIdx.y; a + 1 < v; a += gridDim.y) {
+        const size_t q0 = (size_t) a * v - (size_t) a * (a + 1) / 2 - (a + 1);
+        for (int b = a + 1 + threadIdx.x; b < v; b += blockDim.x) d[q0 + b] -= x[(size_t) a * v + b] - x[(size_t) b * v + a];
+    }
+}
+void packed_antisym_sub(Ctx &ctx, const double *X, int npo, int v, double *LP, long long ld) {
+    if (npo <= 0 || v < 2) return;
+    const unsigned ny = (unsigned) std::min(v - 1, (8 * ctx.sm_count + npo - 1) / npo);
+    packed_antisym_sub_kernel<<<dim3((unsigned) npo, ny), v >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(X, v, LP, ld);
+    ctx.launched("packed_antisym_sub");
 }
 
 __global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, long long npv, int o, int v, double *__restrict__ r) {

@@ -23,7 +23,7 @@ void make_fock(Ctx &ctx, const double *e1, const double *e2, int n1, int n2, dou
 // cc.cpp elementwise pieces
 void make_tau(Ctx &ctx, const double *Ts, const double *Td, int o, int v, bool bar, double *out);
 void multiply_Ts(Ctx &ctx, const double *Ts, int o, int v, double *out);
-// out[j,b,n,f] = -1/2 Td[j,n,f,b] - Ts[j,f] Ts[n,b]   (cc.cpp:247 + :249 as one operand)
+// out[j,b,n,f] = -1/2 Td[j,n,f,b] - Ts[j,f] Ts[n,b]   (cc.cpp:247 + :249 as one operand); Ts == nullptr: -1/2 Td only
 void wmbej_amplitudes(Ctx &ctx, const double *Ts, const double *Td, int o, int v, double *out);
 void add_offdiag(Ctx &ctx, double *F, const double *Fadd, int n);// F(a,e) += (1-d_ae) Fadd(a,e)
 void make_D_ia(Ctx &ctx, const double *foo, const double *fvv, int o, int v, double *D);
@@ -47,6 +47,16 @@ void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out);
 void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld);
 // r[i,j,a,b] += sgn(ij) sgn(ab) LP[p(i,j)][p(a,b)]  (zero on the diagonals); LP is [o(o-1)/2][v(v-1)/2]
 void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, double *r);
+
+// packed-pair pieces of the fused CCSD iteration (i<j rows, a<b columns; `ld` = row stride, even)
+void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,
+              bool bar = false);// rows = any list of (i,j) pairs; bar: tau-bar (Stanton eq. 10)
+void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, double *F);
+void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *LP, long long ldl,
+                 const double *foo, const double *fvv, const double *D, int o, int v, double *out);
+void wmnij_pack(Ctx &ctx, const double *W, int o, const int *pairs_o, int npo, double *dst, long long ld);
+void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, double alpha, double *W);
+void packed_antisym_sub(Ctx &ctx, const double *X, int npo, int v, double *LP, long long ld);
 
 // max |x + P x| over an index-pair transposition, relative to max|x| -> host values
 void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,

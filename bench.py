@@ -295,7 +295,85 @@ def cublas_fp64_peak(torch, n=8192):
     return fl / burst / 1e12, fl / sustained / 1e12
 
 
-def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=8, cpu_sample=False, sharded=False):
+LAUNCH_LISTS = ("profiles/r2_launches_ccsd.csv",)
+
+
+def ccsd_roofline(torch, qcp2_b200, ctx, so, foo, fov, fvv, guess, T1, T2, o, v, s_per_iter, peak_tflops):
+    """Roofline of one CCSD iteration of the formulation actually RUN (pair-packed ladder family, factorised t1.t1
+    terms): the library records every product of one iteration (qcp2_gemm_log); from that record
+      executed flops = sum 2 M N K, operand bytes = sum 8 (M K + K N + M N (1 + [beta != 0])) (each operand once),
+      bound = sum over products of max(flops / FP64 peak, bytes / HBM) -- the time a perfect kernel per product needs.
+    The dominant kernel (the packed tau product against [<ab||ef>; <am||ef>; <mn||ef>]) is then timed alone, live,
+    with CUDA events at its recorded shape, and the per-kernel shares of a tracked ncu launch list are attached."""
+    import ctypes as C
+    p = qcp2_b200._p
+    n2 = o + v
+    E, it = C.c_double(), C.c_int()
+    ctx.gemm_log(True)
+    ctx.check(ctx.lib.qcp2_ccsd(ctx.h, p(so), n2, None, p(foo), p(fov), p(fvv), p(guess), o, v, 2, C.c_double(0.0),
+                                p(T1), p(T2), C.byref(E), C.byref(it), None, None))
+    recs = ctx.gemm_log_read()
+    ctx.gemm_log(False)
+    hbm = 6459.6e9
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] * 1e9
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        hbm_src = "round-1 MEASURED_PEAKS.json value (file absent on this box)"
+    peak = (peak_tflops or 35.4) * 1e12
+    fl = by = bound = 0.0
+    dom = None
+    for r in recs:
+        f = 2.0 * r["M"] * r["N"] * r["K"] * r["batch"]
+        b = 8.0 * (r["M"] * r["K"] + r["K"] * r["N"] + r["M"] * r["N"] * (2 if r["beta"] else 1)) * r["batch"]
+        fl, by, bound = fl + f, by + b, bound + max(f / peak, b / hbm)
+        if dom is None or f > dom[0]:
+            dom = (f, r)
+    res = {"executed_gflop_per_iter": fl / 1e9, "operand_gbytes_per_iter": by / 1e9, "products_per_iter": len(recs),
+           "bound_s_per_iter": bound, "frac_of_bound": bound / s_per_iter if s_per_iter else None,
+           "executed_tflops": fl / s_per_iter / 1e12 if s_per_iter else None,
+           "peaks": {"fp64_tflops": peak / 1e12, "fp64_source": "cuBLAS DGEMM 8192^3 measured in this run (sustained)" if peak_tflops else "35.4 (round-1 yardstick; --no-peak)",
+                     "hbm_gbs": hbm / 1e9, "hbm_source": hbm_src},
+           "note": "bound counts the GEMMs only (each operand streamed once at the measured HBM rate, flops at the measured cuBLAS FP64 "
+                   "rate); the ~25 elementwise / packing kernels of an iteration are not in it"}
+    if dom:
+        f, r = dom
+        M, N, K = r["M"], r["N"], r["K"]
+        ld = K + (K & 1)
+        fdev = dict(dtype=torch.float64, device="cuda")
+        A = torch.randn((M, ld), **fdev)
+        B = torch.randn((N, ld), **fdev)
+        Cm = torch.empty((M, N + (N & 1)), **fdev)
+        torch.cuda.current_stream().synchronize()
+        ctx.dgemm_ex(0, 1, M, N, K, 1.0, A, ld, B, ld, 0.0, Cm, N + (N & 1), reps=2)
+        t = ctx.dgemm_ex(0, 1, M, N, K, 1.0, A, ld, B, ld, 0.0, Cm, N + (N & 1), reps=10)
+        res["dominant_kernel"] = {"kernel": "ws_dgemm_kernel<WsShape<1,8,6,4>,A [M][K],B [N][K]> (48x256 CTA tile, 5-stage TMA/mbarrier ring, "
+                                            "8 DMMA.8x8x4 consumer warps, in-kernel ordered split-K)",
+                                  "what": "packed tau [i<j][e<f] x [<ab||ef>; <am||ef>; <mn||ef>]^T", "M": M, "N": N, "K": K,
+                                  "tile": [r["tile_m"], r["tile_n"]], "split_k": r["split"], "avg_us": t * 1e6, "tflops": f / t / 1e12,
+                                  "frac": f / t / peak, "bound": "tensor",
+                                  "alg_flops_per_launch": f, "timed": "alone, 10 launches, CUDA events on the launching stream"}
+        del A, B, Cm
+    for rel in LAUNCH_LISTS:
+        path = os.path.join(ROOT, rel)
+        if os.path.exists(path):
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import launch_table
+            seq = launch_table.load(path)
+            idx = [i for i, (n, _, _) in enumerate(seq) if n.startswith("ccsd_energy")]
+            one = seq[idx[-2]:idx[-1]] if len(idx) >= 2 else seq
+            tot = sum(t for _, t, _ in one)
+            agg = {}
+            for n, t, _ in one:
+                agg[n] = agg.get(n, 0.0) + t
+            res["launch_list"] = {"file": rel, "launches": len(one), "serialised_us": tot,
+                                  "top": [{"kernel": n, "us": t, "share": t / tot} for n, t in sorted(agg.items(), key=lambda x: -x[1])[:8]]}
+            break
+    return res
+
+
+def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=8, cpu_sample=False, sharded=False, roofline=False,
+                          peak_tflops=None):
     """Secondary metric: CCSD seconds/iteration on the CH4/cc-pVTZ shape (o=10, v=162).  The integrals are a
     random-init spin-orbital tensor <pq||rs> with the permutational symmetries every real input has
     (antisymmetric in pq and in rs, symmetric under pq<->rs); it is sliced on the device and iterated through
@@ -331,6 +409,8 @@ def ccsd_seconds_per_iter(torch, qcp2_b200, ctx, o=10, v=162, iters=8, cpu_sampl
     out = {"s_per_iter": secs[-1], "o": o, "v": v, "iters_timed": iters, "tflops_reference_formulation": flops / secs[-1] / 1e12,
            "data": "random-init antisymmetrised <pq||rs>, CH4/cc-pVTZ shape", "launches_per_iter": (ctx.kernel_launches - launches0) // (2 * iters),
            "e_after_iters": E.value if math.isfinite(E.value) else None}
+    if roofline and not sharded:
+        out["roofline"] = ccsd_roofline(torch, qcp2_b200, ctx, so, foo, fov, fvv, guess, T1, T2, o, v, secs[-1], peak_tflops)
     if cpu_sample:
         # one iteration of the numpy/einsum CPU port (BLAS on all host cores) on the same blocks
         from oracle import np_oracle as npo
@@ -527,7 +607,8 @@ def main():
     ccsd = None
     if not args.no_ccsd and (rank == 0 or world > 1):
         try:  # N > 1: collective (row/column-sharded products of every iteration over the library's communicator)
-            ccsd = ccsd_seconds_per_iter(torch, qcp2_b200, ctx, cpu_sample=(world == 1 and not args.no_cpu_baseline), sharded=(world > 1))
+            ccsd = ccsd_seconds_per_iter(torch, qcp2_b200, ctx, cpu_sample=(world == 1 and not args.no_cpu_baseline), sharded=(world > 1),
+                                         roofline=(world == 1), peak_tflops=peak_sus or None)
             ccsd["parallelism"] = ("single GPU" if world == 1 else
                                    "large products of each iteration split over %d ranks along their longer free dimension, one "
                                    "ncclAllGather each (qcp2_set_ccsd_sharding); everything else replicated" % world)

@@ -197,6 +197,9 @@ int qcp2_t_plan_run(qcp2_t_plan *plan, long long first, long long stride, long l
 /* device time of the GEMM kernels / all kernels of the last qcp2_t_plan_run (seconds, CUDA events) */
 int qcp2_t_plan_timings(const qcp2_t_plan *plan, double *gemm_seconds, double *total_seconds, long long *gemm_launches,
                         long long *all_launches);
+/* which kernel the plan's triples GEMM runs on (1 = the TMA/mbarrier kernel), the logical column count of X
+ * (v(v-1)/2 or v^2), its padded row stride and the triples per launch; any pointer may be NULL */
+int qcp2_t_plan_info(const qcp2_t_plan *plan, int *uses_tma_kernel, long long *ncols, long long *row_stride, int *triples_per_batch);
 int qcp2_t_plan_destroy(qcp2_t_plan *plan);
 
 /* Fused pipeline main.cpp:76-88 runs after the SCF: MP2 -> CCSD -> (T) with every tensor resident
@@ -227,6 +230,12 @@ int qcp2_dgemm(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, doubl
 int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A, long long lda,
                   const double *B, long long ldb, double beta, double *C, long long ldc, int batch, long long strideA,
                   long long strideB, long long strideC, int tile, int k_splits, int reps, double *seconds);
+/* Record of the products the library launches (measurement only).  enable != 0 starts / clears the record; inside
+ * qcp2_ccsd / qcp2_post_hf the record is restarted at every iteration, so after the call it holds the products of ONE
+ * iteration.  qcp2_gemm_log_read copies up to cap records of 8 values {M, N, K, batch, beta != 0, tile_m (negative:
+ * cp.async kernel), tile_n, split_k} and returns the number of records held. */
+int qcp2_gemm_log(qcp2_ctx *ctx, int enable);
+long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap);
 /* products run so far on the warp-specialised TMA kernel (return value) and on the cp.async kernel (*legacy) */
 long long qcp2_gemm_counts(const qcp2_ctx *ctx, long long *legacy);
 /* counter-based synthetic (T) inputs of SURVEY.md section 8d, generated on the device

@@ -799,6 +799,15 @@ int qcp2_t_plan_timings(const qcp2_t_plan *plan, double *gemm_seconds, double *t
     return 0;
 }
 
+int qcp2_t_plan_info(const qcp2_t_plan *plan, int *uses_tma_kernel, long long *ncols, long long *row_stride, int *triples_per_batch) {
+    if (!plan) return 2;
+    if (uses_tma_kernel) *uses_tma_kernel = plan->plan->use_tma ? 1 : 0;
+    if (ncols) *ncols = plan->plan->ncols;
+    if (row_stride) *row_stride = plan->plan->ld;
+    if (triples_per_batch) *triples_per_batch = plan->plan->tb;
+    return 0;
+}
+
 int qcp2_t_plan_destroy(qcp2_t_plan *plan) {
     if (!plan) return 0;
     cudaSetDevice(plan->owner->c.device);
@@ -1025,6 +1034,24 @@ int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, do
         if (seconds) *seconds = 1e-3 * ms / std::max(reps, 1);
         c.sync();
     });
+}
+
+int qcp2_gemm_log(qcp2_ctx *ctx, int enable) {
+    if (!ctx) return 2;
+    ctx->c.log_gemms = enable != 0;
+    ctx->c.gemm_log.clear();
+    return 0;
+}
+
+long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap) {
+    if (!ctx) return 0;
+    const long long n = (long long) ctx->c.gemm_log.size();
+    for (long long k = 0; recs && k < n && k < cap; ++k) {
+        const Ctx::GemmRec &r = ctx->c.gemm_log[(size_t) k];
+        const long long v[8] = {r.M, r.N, r.K, r.batch, r.beta, r.tile_m, r.tile_n, r.split};
+        for (int q = 0; q < 8; ++q) recs[8 * k + q] = v[q];
+    }
+    return n;
 }
 
 long long qcp2_gemm_counts(const qcp2_ctx *ctx, long long *legacy) {

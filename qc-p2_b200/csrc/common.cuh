@@ -69,6 +69,13 @@ struct Ctx {
     unsigned int *ws_counters = nullptr;
     int ws_counters_cap = 0;
     long long ws_gemms = 0, legacy_gemms = 0;
+    // optional record of the products gemm() launches (qcp2_gemm_log): bench.py derives the executed flops and the
+    // operand bytes of one CCSD iteration from it
+    struct GemmRec {
+        int M, N, K, batch, beta, tile_m, tile_n, split;
+    };
+    std::vector<GemmRec> gemm_log;
+    bool log_gemms = false;
     // device offset tables of the GEMM's scatter epilogue, keyed by the contraction's signature (contract.cu); they
     // live as long as the context, so a table made in an eager iteration is there when the same call is captured
     struct OffsetTable {

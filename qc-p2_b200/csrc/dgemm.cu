@@ -232,6 +232,8 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
         if (trace)
             fprintf(stderr, "[qcp2 gemm] M %d N %d K %d batch %d  a_kc %d b_nc %d -> ws tile %dx%d%s split %d\n", g.M, g.N, g.K, g.batch,
                     (int) a_kc, (int) b_nc, kWsShapes[ch.shape].bm, kWsShapes[ch.shape].bn, ch.swap ? " (transposed)" : "", ch.split);
+        if (ctx.log_gemms)
+            ctx.gemm_log.push_back(Ctx::GemmRec{g.M, g.N, g.K, g.batch, g.beta != 0.0, kWsShapes[ch.shape].bm, kWsShapes[ch.shape].bn, ch.split});
         ws_run(ctx, g, a_kc, b_nc, ch.shape, ch.swap, ch.split);
         return;
     }
@@ -292,6 +294,7 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     if (trace)
         fprintf(stderr, "[qcp2 gemm] M %d N %d K %d batch %d  a_kc %d b_nc %d -> tile %dx%d split %d\n", g.M, g.N, g.K, g.batch, (int) a_kc,
                 (int) b_nc, cand[best_t].bm, cand[best_t].bn, best_split);
+    if (ctx.log_gemms) ctx.gemm_log.push_back(Ctx::GemmRec{g.M, g.N, g.K, g.batch, g.beta != 0.0, -cand[best_t].bm, cand[best_t].bn, best_split});
     if (best_t == 6) launch_dgemm_16n(ctx, run, a_kc, b_nc, vec);
     else if (best_t == 5) launch_dgemm_16m(ctx, run, a_kc, b_nc, vec);
     else if (best_t == 4) launch_dgemm_48(ctx, run, a_kc, b_nc, vec);

@@ -327,6 +327,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     // on it is replayed as a CUDA graph (stream capture, incl. the stream-ordered workspace allocations), which
     // removes the launch gaps that dominate small molecules.  QCP2_CCSD_NO_GRAPH=1 keeps the eager path.
     auto body = [&]() {
+        if (ctx.log_gemms) ctx.gemm_log.clear();// the record holds the products of ONE iteration
         if (sym) {
             ccsd_sym_iteration(ctx, I, foo, fov, fvv, o, v, sp, T1, T2, t1n, t2n);         // :442-446
         } else {

@@ -37,28 +37,29 @@ __host__ __device__ __forceinline__ long long pair_index(long long b, long long 
     return b * v - b * (b + 1) / 2 + (c - b - 1);// b < c
 }
 
-// dst[(r1,r0) or (r0,r1)][p(b<c)] = src[r0][r1][b][c]
-__global__ void pack_bc_kernel(const double *__restrict__ src, long long R0, long long R1, int swap01, int v,
-                               double *__restrict__ dst) {
-    const long long np = (long long) v * (v - 1) / 2, n = R0 * R1 * v * v;
+// dst[(r1,r0) or (r0,r1)][q] = src[r0][r1][b][c], rows `ld` doubles apart (ld even: 16-byte rows for the bulk copies);
+// packed: q = p(b<c) (symmetric mode), else q = b v + c (literal mode: every (b,c))
+__global__ void pack_bc_kernel(const double *__restrict__ src, long long R0, long long R1, int swap01, int v, int packed,
+                               long long ld, double *__restrict__ dst) {
+    const long long n = R0 * R1 * v * v;
     GRID_STRIDE(lin, n) {
         long long r = lin;
         const long long c = r % v;
         r /= v;
         const long long b = r % v;
         r /= v;
-        if (b >= c) continue;
+        if (packed && b >= c) continue;
         const long long r1 = r % R1, r0 = r / R1;
         const long long row = swap01 ? r1 * R0 + r0 : r0 * R1 + r1;
-        dst[row * np + pair_index(b, c, v)] = src[lin];
+        dst[row * ld + (packed ? pair_index(b, c, v) : b * v + c)] = src[lin];
     }
 }
 
 // one streamed slab: src[e][b][c] (v^3 doubles, unpacked) -> dst[e][p(b<c)], and the antisymmetry
 // defect max |x[e,b,c] + x[e,c,b]| / max |x| of the slab accumulated into res[0..1]
-__global__ void pack_slab_kernel(const double *__restrict__ src, int v, double *__restrict__ dst,
+__global__ void pack_slab_kernel(const double *__restrict__ src, int v, double *__restrict__ dst, long long np,
                                  unsigned long long *__restrict__ res) {
-    const long long np = (long long) v * (v - 1) / 2, n = (long long) v * v * v;
+    const long long n = (long long) v * v * v;// np = row stride of dst (>= v(v-1)/2, even)
     double defect = 0.0, mx = 0.0;
     GRID_STRIDE(lin, n) {
         long long r = lin;
@@ -196,11 +197,11 @@ __global__ void __launch_bounds__(kBlock) t_energy_kernel(EnergyArgs p) {
                 sum += W * (W + Vv) / (dab - p.ev[c]);
             }
         } else {
-            const double *Xab = X + (a * V + b) * V, *Xba = X + (b * V + a) * V;
+            const double *Xab = X + a * nc + b * V, *Xba = X + b * nc + a * V;// X rows are nc (>= v^2) apart
             const double *ojk_bc = Ojk + b * V, *oik_bc = Oik + b * V, *oji_bc = Oji + b * V;
             const double *ojk_ac = Ojk + a * V, *oik_ac = Oik + a * V, *oji_ac = Oji + a * V;
             for (int c = lane; c < p.v; c += 32) {
-                const double W = Xab[c] - Xba[c] - X[(c * V + b) * V + a];
+                const double W = Xab[c] - Xba[c] - X[c * nc + b * V + a];
                 const double tic = p.T1[i * V + c], tjc = p.T1[j * V + c], tkc = p.T1[k * V + c];
                 const double Ya = tia * ojk_bc[c] - tja * oik_bc[c] - tka * oji_bc[c];
                 const double Yb = tib * ojk_ac[c] - tjb * oik_ac[c] - tkb * oji_ac[c];
@@ -454,6 +455,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     const long long O = o, V = v;
     const bool sym = mode == QCP2_T_SYMMETRIC;
     P->ncols = sym ? V * (V - 1) / 2 : V * V;
+    P->ld = (P->ncols + 1) & ~1LL;// even row stride: every packed row starts on a 16-byte boundary (v = 2, 3 mod 4 included)
     P->ntriples = t_count(o, mode);
     P->T1 = T1, P->T2 = T2, P->oovv = oovv, P->vovv = vovv, P->ovoo = ovoo;
     P->eo = DBuf(ctx, (size_t) o), P->ev = DBuf(ctx, (size_t) v);
@@ -462,19 +464,29 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     for (int s = 0; s < GEMM_MAX_SEG; ++s)
         P->kb_begin[s + 1] = P->kb_begin[s] + (int) (((s < 3 ? V : O) + GEMM_BK - 1) / GEMM_BK);
     P->kpad = P->kb_begin[GEMM_MAX_SEG] * GEMM_BK;
-    if (sym && P->ncols > 0) {
-        const long long np = P->ncols;
+    if (P->ncols > 0) {
+        // Both modes own re-laid copies [i][e][ld] / [i][m][ld] of <vo||vv> and T2 (symmetric: b<c packed; literal: all
+        // (b,c)), so the B rows of every triple are contiguous, 16-byte aligned rows for the TMA kernel's bulk copies.
+        // The pad column (odd v(v-1)/2 or v^2) is zero and is simply computed along.
+        const long long np = P->ld;
         P->vovvP = DBuf(ctx, (size_t) (O * V * np));
         P->T2P = DBuf(ctx, (size_t) (O * O * np));
-        P->oovvP = DBuf(ctx, (size_t) (O * O * np));
+        if (np != P->ncols) {
+            QCP2_CUDA(cudaMemsetAsync(P->vovvP.p, 0, (size_t) (O * V * np) * 8, ctx.stream));
+            QCP2_CUDA(cudaMemsetAsync(P->T2P.p, 0, (size_t) (O * O * np) * 8, ctx.stream));
+        }
+        if (sym) {
+            P->oovvP = DBuf(ctx, (size_t) (O * O * np));
+            if (np != P->ncols) QCP2_CUDA(cudaMemsetAsync(P->oovvP.p, 0, (size_t) (O * O * np) * 8, ctx.stream));
+        }
         auto pack = [&](const double *src, long long R0, long long R1, int swap, double *dst) {
-            pack_bc_kernel<<<grid_for(R0 * R1 * V * V, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(src, R0, R1, swap,
-                                                                                                   v, dst);
+            pack_bc_kernel<<<grid_for(R0 * R1 * V * V, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(src, R0, R1, swap, v, sym ? 1 : 0,
+                                                                                                   np, dst);
             ctx.launched("pack_bc");
         };
-        if (!ts) pack(vovv, V, O, 1, P->vovvP);// [e][i][b][c] -> [i][e][p]
-        pack(T2, O, O, 0, P->T2P);    // [i][m][b][c] -> [i][m][p]
-        pack(oovv, O, O, 0, P->oovvP);
+        if (!ts) pack(vovv, V, O, 1, P->vovvP);// [e][i][b][c] -> [i][e][q]
+        pack(T2, O, O, 0, P->T2P);    // [i][m][b][c] -> [i][m][q]
+        if (sym) pack(oovv, O, O, 0, P->oovvP);
         if (ts) {
             const bool multi = ts->comm && ts->comm->nranks > 1;
             const bool is_root = !multi || ts->comm->rank == ts->root;
@@ -499,7 +511,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
                     // vovv[e][i][b][c]: v rows of v^2 doubles, o*v^2 apart -> stage[e][b][c]
                     QCP2_CUDA(cudaMemcpy2DAsync(P->stage.p, (size_t) (V * V) * 8, ts->vovv_host + i * V * V, (size_t) (O * V * V) * 8,
                                                 (size_t) (V * V) * 8, (size_t) V, cudaMemcpyHostToDevice, P->copy));
-                    pack_slab_kernel<<<grid_for(V * V * V, kBlock, ctx.sm_count, 4), kBlock, 0, P->copy>>>(P->stage.p, v, slabP,
+                    pack_slab_kernel<<<grid_for(V * V * V, kBlock, ctx.sm_count, 4), kBlock, 0, P->copy>>>(P->stage.p, v, slabP, np,
                                                                                                          P->vovv_defect);
                     ctx.launched("pack_slab");
                 }
@@ -534,14 +546,14 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     // batch size: enough CTAs for ~48 full waves, bounded by a 4 GB X buffer
     const long long tiles = ((V + TileT::kBM - 1) / TileT::kBM) * ((std::max<long long>(P->ncols, 1) + TileT::kBN - 1) / TileT::kBN);
     long long tb = (48LL * ctx.sm_count + tiles - 1) / tiles;
-    const long long xbytes = std::max<long long>(V * P->ncols * 8, 8);
+    const long long xbytes = std::max<long long>(V * P->ld * 8, 8);
     tb = std::min(tb, std::max<long long>(1, (4LL << 30) / xbytes));
     tb = std::max<long long>(1, std::min<long long>(tb, std::min<long long>(4096, std::max<long long>(P->ntriples, 1))));
     if (const char *env = getenv("QCP2_T_BATCH")) tb = std::max<long long>(1, std::min<long long>(atoll(env), std::max<long long>(P->ntriples, 1)));// experiments
     P->tb = (int) tb;
     {
         if (sym) {// work items (a, bt <= ct) of the tiled energy sweep
-            QCP2_REQUIRE(V * P->ncols < (1LL << 31), "(T): v * v(v-1)/2 must stay below 2^31");
+            QCP2_REQUIRE(V * P->ld < (1LL << 31), "(T): v * v(v-1)/2 must stay below 2^31");
             std::vector<int> items;
             for (int a = 0; a + 2 < v; ++a) {
                 const int nt = (v - a - 1 + 31) / 32;
@@ -559,15 +571,14 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     {
         const char *env = getenv("QCP2_T_GEMM");// "cpasync" forces the non-TMA kernel (A/B experiments)
         const bool want_tma = !(env && std::string(env) == "cpasync");
-        const bool rows_aligned = (P->ncols % 2 == 0) && ((reinterpret_cast<uintptr_t>(P->vovvP.p) & 15) == 0) &&
-                                  ((reinterpret_cast<uintptr_t>(P->T2P.p) & 15) == 0);
-        P->use_tma = sym && want_tma && rows_aligned;
+        const bool rows_aligned = ((reinterpret_cast<uintptr_t>(P->vovvP.p) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P->T2P.p) & 15) == 0);
+        P->use_tma = want_tma && rows_aligned && P->ncols > 0;// both modes; the cp.async SEG kernel stays as an A/B option
         const long long mtiles = (V + TG_BM - 1) / TG_BM;
         P->a_per_triple = P->use_tma ? mtiles * (P->kpad / GEMM_BK) * TG_BM * TG_ALD : V * P->kpad;
     }
     for (int s = 0; s < 2; ++s) {
         P->Abuf[s] = DBuf(ctx, (size_t) (tb * P->a_per_triple));
-        P->Xbuf[s] = DBuf(ctx, (size_t) (tb * V * std::max<long long>(P->ncols, 1)));
+        P->Xbuf[s] = DBuf(ctx, (size_t) (tb * V * std::max<long long>(P->ld, 1)));
         P->partial[s] = DBuf(ctx, (size_t) (tb * P->blocks_per_triple));
         QCP2_CUDA(cudaEventCreateWithFlags(&P->gemm_done[s], cudaEventDisableTiming));
         QCP2_CUDA(cudaEventCreateWithFlags(&P->energy_done[s], cudaEventDisableTiming));
@@ -627,7 +638,7 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
     const long long launches0 = ctx.launches;
     if (count == 0 || P.ncols == 0) return;
     const bool sym = P.mode == QCP2_T_SYMMETRIC;
-    const long long O = P.o, V = P.v, nc = P.ncols;
+    const long long O = P.o, V = P.v, nc = P.ld;// row stride of the packed tensors and of X (the pad column is computed along)
 
     // host-side descriptors for the whole run
     std::vector<int> ijk((size_t) (3 * count));
@@ -658,8 +669,8 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         triple_of(t, P.o, sym, x);
         for (int s = 0; s < 3; ++s) {
             const long long occ = x[s];
-            seg[(size_t) q].B[s] = sym ? P.vovvP.p + occ * V * nc : P.vovv + occ * V * V;
-            seg[(size_t) q].B[3 + s] = sym ? P.T2P.p + occ * O * nc : P.T2 + occ * O * V * V;
+            seg[(size_t) q].B[s] = P.vovvP.p + occ * V * nc;
+            seg[(size_t) q].B[3 + s] = P.T2P.p + occ * O * nc;
         }
         for (int s = 0; s < GEMM_MAX_SEG; ++s)
             aligned = aligned && ((reinterpret_cast<uintptr_t>(seg[(size_t) q].B[s]) & 15) == 0);
@@ -723,7 +734,7 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
             for (int q = 0; q <= GEMM_MAX_SEG; ++q) g.seg_kb_begin[q] = P.kb_begin[q];
             for (int q = 0; q < GEMM_MAX_SEG; ++q) {
                 g.seg_rows[q] = q < 3 ? P.v : P.o;
-                g.seg_ldb[q] = sym ? nc : (q < 3 ? O * V * V : V * V);
+                g.seg_ldb[q] = nc;
             }
             gemm(ctx, g, true, true);
         }

@@ -29,11 +29,12 @@ struct TPlan {
     Ctx *ctx = nullptr;
     int o = 0, v = 0, mode = 0;     // mode: QCP2_T_LITERAL or QCP2_T_SYMMETRIC
     long long ncols = 0;            // v*v (literal) or v(v-1)/2 (symmetric, b<c packed)
+    long long ld = 0;               // row stride of the re-laid tensors and of X: ncols rounded up to even
     long long ntriples = 0;         // o^3 or C(o,3)
     int kpad = 0;                   // padded K of the per-triple GEMM
     int kb_begin[GEMM_MAX_SEG + 1] = {0, 0, 0, 0, 0, 0, 0};
-    // inputs (device).  literal mode reads the caller's tensors in place; symmetric mode
-    // owns b<c packed copies.
+    // inputs (device).  Both modes own re-laid copies of <vo||vv> and T2 with contiguous, 16-byte aligned B rows
+    // (symmetric: b<c packed; literal: every (b,c)); T1, <oo||vv> (literal) and <ov||oo> are read in place.
     const double *T1 = nullptr, *T2 = nullptr, *oovv = nullptr, *vovv = nullptr, *ovoo = nullptr;
     DBuf eo, ev, vovvP, T2P, oovvP;
     // double-buffered per-batch workspace
@@ -58,7 +59,7 @@ struct TPlan {
     std::vector<cudaEvent_t> slab_ready;  // one per occupied index
     DBuf stage;
     unsigned long long *vovv_defect = nullptr;// device [2]: max |x[e,b,c] + x[e,c,b]|, max |x| over the slabs
-    bool use_tma = false;           // symmetric mode with 16-byte aligned packed rows
+    bool use_tma = false;           // the TMA/mbarrier kernel (t_gemm_tma.cu) runs the triples GEMM (both modes)
     long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
     ~TPlan();
 };

@@ -47,6 +47,7 @@ def load_library():
         lib.qcp2_ccsd_last_loop_seconds.restype = C.c_double
         lib.qcp2_sharded_gemms.restype = C.c_longlong
         lib.qcp2_gemm_counts.restype = C.c_longlong
+        lib.qcp2_gemm_log_read.restype = C.c_longlong
         _lib = lib
     return _lib
 
@@ -417,6 +418,17 @@ class Context:
                                           int(k_splits), int(reps), C.byref(secs)))
         return secs.value
 
+    def gemm_log(self, enable=True):
+        self.check(self.lib.qcp2_gemm_log(self.h, int(bool(enable))))
+
+    def gemm_log_read(self):
+        """Products of the last recorded CCSD iteration: list of dicts M, N, K, batch, beta, tile_m, tile_n, split."""
+        n = int(self.lib.qcp2_gemm_log_read(self.h, None, C.c_longlong(0)))
+        buf = (C.c_longlong * (8 * max(n, 1)))()
+        self.lib.qcp2_gemm_log_read(self.h, buf, C.c_longlong(n))
+        keys = ("M", "N", "K", "batch", "beta", "tile_m", "tile_n", "split")
+        return [dict(zip(keys, buf[8 * k:8 * k + 8])) for k in range(n)]
+
     def gemm_counts(self):
         """(products on the warp-specialised TMA kernel, products on the cp.async kernel) so far."""
         legacy = C.c_longlong()
@@ -464,6 +476,12 @@ class DeviceTriples:
         self.ctx.check(self.ctx.lib.qcp2_t_plan_run(self.h, C.c_longlong(first), C.c_longlong(stride),
                                                     C.c_longlong(max_count), _p(e_triples), C.byref(E)))
         return E.value
+
+    def info(self):
+        tma, tb = C.c_int(), C.c_int()
+        nc, ld = C.c_longlong(), C.c_longlong()
+        self.ctx.check(self.ctx.lib.qcp2_t_plan_info(self.h, C.byref(tma), C.byref(nc), C.byref(ld), C.byref(tb)))
+        return {"uses_tma_kernel": bool(tma.value), "ncols": nc.value, "row_stride": ld.value, "triples_per_batch": tb.value}
 
     def timings(self):
         g, t = C.c_double(), C.c_double()

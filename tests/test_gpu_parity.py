@@ -253,7 +253,7 @@ def test_ccsd_from_presliced_blocks_and_maxiter_cap(ctx):
 
 
 # ---------------------------------------------------------------------------- (T)
-@pytest.mark.parametrize("o,v", [(3, 4), (4, 6), (5, 17), (6, 33)])
+@pytest.mark.parametrize("o,v", [(3, 4), (4, 6), (4, 7), (5, 17), (6, 33), (3, 39)])  # v(v-1)/2 odd for v = 6, 7; v^2 odd for 7, 17, 33, 39
 def test_t_synthetic_small_all_modes(ctx, o, v):
     s = npo.synthetic_t_inputs(o, v)
     args = (s["T1"], s["T2"], s["oovv"], s["vovv"], s["ovoo"], s["eps_o"], s["eps_v"])
@@ -262,6 +262,32 @@ def test_t_synthetic_small_all_modes(ctx, o, v):
         got = ctx.CCSD_T(*args, mode)
         assert abs(got - ref) < E_TOL and abs(got - ref) < 1e-12 * abs(ref), (mode, got, ref)
     assert ctx.t_select_mode(s["T2"], s["oovv"], s["vovv"], s["ovoo"]) == qcp2_b200.T_SYMMETRIC
+
+
+def test_t_tma_kernel_serves_every_v_and_both_modes(ctx):
+    """v = 162 (CH4/cc-pVTZ: v(v-1)/2 = 13 041 is odd) and the literal mode (N = v^2) run on the TMA/mbarrier kernel: the
+    packed rows are padded to an even stride.  Checked against the per-triple numpy restatement."""
+    import torch
+    o, v = 4, 162
+    s = npo.synthetic_t_inputs(o, v)
+    names = ("T1", "T2", "oovv", "vovv", "ovoo", "eps_o", "eps_v")
+    ref = npo.ccsd_t_blocked(*(s[k] for k in names), True)
+    got = ctx.CCSD_T(*(s[k] for k in names), qcp2_b200.T_SYMMETRIC)
+    assert abs(got - ref) < 1e-12 * abs(ref), (got, ref)
+    got_lit = ctx.CCSD_T(*(s[k] for k in names), qcp2_b200.T_LITERAL)
+    assert abs(got_lit - ref) < 1e-11 * abs(ref), (got_lit, ref)
+    ctx.set_pointer_mode(qcp2_b200.DEVICE)
+    try:
+        d = {k: torch.tensor(s[k], device="cuda") for k in names}
+        for mode, ncols in ((qcp2_b200.T_SYMMETRIC, v * (v - 1) // 2), (qcp2_b200.T_LITERAL, v * v)):
+            plan = qcp2_b200.DeviceTriples(ctx, *(d[k] for k in names), mode)
+            info = plan.info()
+            assert info["uses_tma_kernel"] and info["ncols"] == ncols and info["row_stride"] % 2 == 0
+            e = plan.run(0, 1, 3)
+            assert np.isfinite(e)
+            plan.close()
+    finally:
+        ctx.set_pointer_mode(qcp2_b200.HOST)
 
 
 def test_t_no_triples_and_unsymmetric_inputs(ctx):

@@ -236,6 +236,13 @@ int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, do
  * cp.async kernel), tile_n, split_k} and returns the number of records held. */
 int qcp2_gemm_log(qcp2_ctx *ctx, int enable);
 long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap);
+/* slice_ints(transform_to_so(aa, bb, ab), o, v, spec) without the (2n)^4 tensor: the o/v block is gathered straight from
+ * the spatial MO tensors (integrals.cpp:136-167 + 184-207 fused; bit-identical values).  out has the block's extents. */
+int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec,
+                  double *out);
+/* High-water mark (bytes) of the context's workspace pool since the start of the last qcp2_post_hf / qcp2_post_hf_mgpu
+ * call: the peak device memory the fused pipeline needed (caller-owned device buffers not included); -1 if unknown. */
+long long qcp2_pool_high_water(const qcp2_ctx *ctx);
 /* products run so far on the warp-specialised TMA kernel (return value) and on the cp.async kernel (*legacy) */
 long long qcp2_gemm_counts(const qcp2_ctx *ctx, long long *legacy);
 /* counter-based synthetic (T) inputs of SURVEY.md section 8d, generated on the device

@@ -865,20 +865,15 @@ void post_hf_impl(Ctx &c, Comm *cm, int root, const double *ao_ints, const doubl
     const double *pea = ea.p, *peb = uhf ? eb.p : ea.p;
     DBuf t2_mp2(c, (size_t) std::max<long long>(o2v2, 1));
     IntsDev I;
-    DBuf blocks[I_COUNT];
-    {
-        DBuf so(c, (size_t) (16 * n4));
-        tr.mark("stage AO integrals + allocate <pq||rs>");
-        mp2_dev(c, ao, ca, uhf ? cb.p : ca.p, pea, peb, n, o, v, uhf != 0, so, t2_mp2, e_mp2);// mp2.cpp:45-86
-        tr.mark("AO->MO, to_so, MP2");
-        if (stages >= 2)
-            for (int k = 0; k < I_COUNT; ++k) {// get_integrals, cc.cpp:8-23
-                blocks[k] = DBuf(c, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
-                slice_block(c, so, n2, o, v, kIntNames[k], blocks[k]);
-                I.p[k] = blocks[k].p;
-            }
-    }// the (2n)^4 tensor is released here
-    tr.mark("slice the 11 blocks");
+    DBuf blocks[I_COUNT], spatial[3];
+    SoSource src;
+    QCP2_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrUsedMemHigh, &c.pool_reset_value));// peak-memory report of this call
+    tr.mark("stage AO integrals");
+    // mp2.cpp:45-86 and get_integrals (cc.cpp:8-23) without the (2n)^4 tensor and without <vv||vv>: every block is gathered
+    // straight from the spatial MO tensors, which stay alive for the CCSD setup (it packs or builds <vv||vv> from them)
+    mp2_blocks_dev(c, ao, ca, uhf ? cb.p : ca.p, pea, peb, n, o, v, uhf != 0, stages >= 2, blocks, I, spatial, src, t2_mp2, e_mp2);
+    tr.mark("AO->MO, the o/v blocks, MP2");
+    (void) n2;
     if (stages < 2) return;
     DBuf foo(c, (size_t) (O * O)), fvv(c, (size_t) (V * V)), F(c, (size_t) ((long long) n2 * n2));
     make_so_moes(c, pea, peb, n, F);// same diagonal as make_fock(eps_a, eps_b, 0, no+nv), cc.cpp:25-34
@@ -899,8 +894,9 @@ void post_hf_impl(Ctx &c, Comm *cm, int root, const double *ao_ints, const doubl
             ShardGuard(Ctx &ctx_, Comm *s) : c(ctx_) { c.shard = s; }
             ~ShardGuard() { c.shard = nullptr; }
         } guard(c, multi && !getenv("QCP2_CCSD_NO_SHARD") ? cm : nullptr);
-        ccsd_dev(c, I, foo, nullptr, fvv, t2_mp2, o, v, maxiter, conv, t1p, t2p, e_ccsd, iters, e_hist);// cc.cpp:409-451
+        ccsd_dev(c, I, foo, nullptr, fvv, t2_mp2, o, v, maxiter, conv, t1p, t2p, e_ccsd, iters, e_hist, &src);// cc.cpp:409-451
     }
+    for (DBuf &sb : spatial) sb.reset();
     t1.finish(), t2.finish();
     tr.mark("CCSD iterations");
     if (stages >= 3) {// cc.cpp:454-560
@@ -1052,6 +1048,30 @@ long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap
         for (int q = 0; q < 8; ++q) recs[8 * k + q] = v[q];
     }
     return n;
+}
+
+int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec, double *out) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(aa && bb && ab && spec && out && n >= 1 && strlen(spec) == 4, "so_block: bad argument");
+        const long long n4 = ipow4(n);
+        long long total = 1;
+        for (int d = 0; d < 4; ++d) total *= (spec[d] == 'o') ? o : v;
+        In a(c, aa, n4), b(c, bb, n4), m(c, ab, n4);
+        Out res(c, out, total);
+        so_block(c, a, b, m, n, o, v, spec, res);
+        res.finish();
+        c.sync();
+    });
+}
+
+long long qcp2_pool_high_water(const qcp2_ctx *ctx) {
+    if (!ctx || !ctx->c.pool) return -1;
+    unsigned long long hi = 0;
+    if (cudaMemPoolGetAttribute(ctx->c.pool, cudaMemPoolAttrUsedMemHigh, &hi) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (long long) hi;
 }
 
 long long qcp2_gemm_counts(const qcp2_ctx *ctx, long long *legacy) {

@@ -38,7 +38,7 @@ TView int_view4(const IntsDev &I, int k, int o, int v) {
 long long even(long long n) { return (n + 1) & ~1LL; }
 }// namespace
 
-bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp) {
+bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp, const SoSource *src) {
     const long long O = o, V = v;
     if (o < 2 || v < 2 || getenv("QCP2_CCSD_DENSE")) return false;
     Trace tr(ctx, "ccsd sym_setup");
@@ -48,7 +48,10 @@ bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v,
     auto check = [&](const double *x, long long d0, long long d1, long long d2, long long d3, int pair) {
         antisymmetry_defect_async(ctx, x, d0, d1, d2, d3, pair, chk + 2 * nchk++);
     };
-    check(I.p[I_VVVV], V, V, V, V, 0), check(I.p[I_VVVV], V, V, V, V, 1);// <ab||ef>: a<b rows, e<f columns
+    const bool direct = I.p[I_VVVV] == nullptr;// <ab||ef> is evaluated from the spatial MO tensors, never stored unpacked
+    QCP2_REQUIRE(!direct || (src && src->aa && src->bb && src->ab), "ccsd: <vv||vv> missing and no spatial integrals to build it from");
+    if (direct) so_vvvv_defect_async(ctx, src->aa, src->bb, src->ab, src->n, o, v, chk), nchk = 2;
+    else check(I.p[I_VVVV], V, V, V, V, 0), check(I.p[I_VVVV], V, V, V, V, 1);// <ab||ef>: a<b rows, e<f columns
     check(I.p[I_OOVV], O, O, V, V, 0), check(I.p[I_OOVV], O, O, V, V, 1);// <mn||ef>: m<n, e<f
     check(I.p[I_VOVV], V, O, V, V, 1);                                  // <am||ef>: e<f
     check(I.p[I_OOOO], O, O, O, O, 0), check(I.p[I_OOOO], O, O, O, O, 1);// W_mnij: m<n, i<j
@@ -89,7 +92,8 @@ bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v,
     sp.offZ = even(sp.npv), sp.offY = sp.offZ + even(V * O), sp.ntot = sp.offY + sp.npo, sp.ldl = even(sp.ntot);
     sp.ladB = DBuf(ctx, (size_t) (sp.ntot * sp.ld));
     QCP2_CUDA(cudaMemsetAsync(sp.ladB.p, 0, (size_t) (sp.ntot * sp.ld) * 8, ctx.stream));
-    pack_pairs(ctx, I.p[I_VVVV], v, v, pd + n_po, sp.npv, sp.ladB.p, sp.ld);
+    if (direct) so_block_packed(ctx, src->aa, src->bb, src->ab, src->n, o, o, o, v, pd + n_po, sp.npv, sp.ladB.p, sp.ld);
+    else pack_pairs(ctx, I.p[I_VVVV], v, v, pd + n_po, sp.npv, sp.ladB.p, sp.ld);
     pack_pairs(ctx, I.p[I_VOVV], o, v, pd + n_pv, (int) (V * O), sp.ladB.p + sp.offZ * sp.ld, sp.ld);// row (a,m) = a*o + m
     pack_pairs(ctx, I.p[I_OOVV], o, v, pd, sp.npo, sp.ladB.p + sp.offY * sp.ld, sp.ld);
     sp.oovvA = DBuf(ctx, (size_t) (O * O * sp.ld));

@@ -88,6 +88,7 @@ struct Ctx {
     // blocks stay cached here instead of in the device's default pool, so the library does not change the behaviour
     // of other cudaMallocAsync users of the process
     cudaMemPool_t pool = nullptr;
+    unsigned long long pool_reset_value = 0;// written to cudaMemPoolAttrUsedMemHigh to restart the high-water mark
 
     double *alloc(size_t n_doubles) { return static_cast<double *>(alloc_bytes((n_doubles ? n_doubles : 1) * sizeof(double))); }
     void *alloc_bytes(size_t n) {

@@ -100,6 +100,37 @@ void mp2_dev(Ctx &ctx, const double *ao, const double *Ca, const double *Cb, con
     ctx.sync();
 }
 
+// mp2.cpp:45-86 + get_integrals (cc.cpp:8-23) for the fused pipeline: the (2n)^4 tensor of transform_to_so and the
+// v^4 block are never built; each o/v block is gathered straight from the spatial MO tensors (same values, bit for bit)
+void mp2_blocks_dev(Ctx &ctx, const double *ao, const double *Ca, const double *Cb, const double *ea, const double *eb, int n, int o,
+                    int v, bool uhf, bool want_blocks, DBuf *blocks, IntsDev &I, DBuf spatial[3], SoSource &src, double *T,
+                    double *e_host) {
+    const long long n4 = (long long) n * n * n * n, n2 = 2LL * n;
+    QCP2_REQUIRE(o >= 0 && v >= 0 && o + v == n2, "MP2: o + v must equal 2n");
+    spatial[0] = DBuf(ctx, (size_t) n4);
+    transform_ao_mo_dev(ctx, ao, Ca, Ca, n, spatial[0]);// mp2.cpp:55 / :71
+    src.aa = src.bb = src.ab = spatial[0].p, src.n = n;
+    if (uhf) {
+        spatial[1] = DBuf(ctx, (size_t) n4), spatial[2] = DBuf(ctx, (size_t) n4);
+        transform_ao_mo_dev(ctx, ao, Cb, Cb, n, spatial[1]);// :72
+        transform_ao_mo_dev(ctx, ao, Ca, Cb, n, spatial[2]);// :73 (Coeff1 = Ca -> k,l ; Coeff2 = Cb -> i,j)
+        src.bb = spatial[1].p, src.ab = spatial[2].p;
+    }
+    for (int k = 0; k < I_COUNT; ++k) {
+        I.p[k] = nullptr;
+        if (k == I_VVVV || (!want_blocks && k != I_OOVV)) continue;
+        blocks[k] = DBuf(ctx, (size_t) std::max<long long>(int_block_size(k, o, v), 1));
+        so_block(ctx, src.aa, src.bb, src.ab, n, o, v, kIntNames[k], blocks[k]);// slice_ints(transform_to_so(..), ..)
+        I.p[k] = blocks[k].p;
+    }
+    DBuf F(ctx, (size_t) (n2 * n2)), den(ctx, (size_t) std::max<long long>((long long) o * o * v * v, 1)), e(ctx, 1);
+    make_so_moes(ctx, ea, uhf ? eb : ea, n, F);
+    make_denom(ctx, F, (int) n2, o, v, den);
+    mp2_amplitudes_energy(ctx, I.p[I_OOVV], den, (long long) o * o * v * v, T, e);
+    QCP2_CUDA(cudaMemcpyAsync(e_host, e.p, sizeof(double), cudaMemcpyDeviceToHost, ctx.stream));
+    ctx.sync();
+}
+
 // ---------------------------------------------------------------------------------
 // cc.cpp:175-255 -- Stanton eqs. 3-8
 // ---------------------------------------------------------------------------------
@@ -281,10 +312,11 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
 
 // cc.cpp:409-451.  Amplitudes, integrals and intermediates never leave the device; the
 // host sees one double per iteration (the energy that decides convergence).
-void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,
+void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fov, const double *fvv,
               const double *T2_guess, int o, int v, int maxiter, double conv, double *T1, double *T2, double *e_host,
-              int *iters_host, double *e_hist_host) {
+              int *iters_host, double *e_hist_host, const SoSource *src) {
     const long long O = o, V = v, o2v2 = O * O * V * V;
+    IntsDev I = I_in;
     DBuf xbuf[X_COUNT];
     InterDev X;
     for (int k = 0; k < X_COUNT; ++k) {
@@ -299,8 +331,16 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, 
     // antisymmetry, SURVEY.md Q5 -- keeps the dense term list below.
     Trace tr(ctx, "ccsd_dev");
     SymPack sp;
-    const bool sym = sym_setup(ctx, I, T2_guess, o, v, sp);
+    const bool sym = sym_setup(ctx, I, T2_guess, o, v, sp, src);
     tr.mark(sym ? "symmetric formulation: checks + packing" : "dense formulation (symmetry checks)");
+    DBuf vvvv_own;
+    if (!sym && I.p[I_VVVV] == nullptr) {// the dense term list reads the v^4 block itself
+        QCP2_REQUIRE(src && src->aa, "ccsd: <vv||vv> missing and no spatial integrals to build it from");
+        vvvv_own = DBuf(ctx, (size_t) std::max<long long>(V * V * V * V, 1));
+        so_block(ctx, src->aa, src->bb, src->ab, src->n, o, v, "vvvv", vvvv_own);
+        I.p[I_VVVV] = vvvv_own.p;
+        tr.mark("<vv||vv> from the spatial integrals");
+    }
     // the integral blocks are constant for the whole loop: their operand re-layouts are made once
     PermCache perm_cache;
     for (int k = 0; k < I_COUNT; ++k)

@@ -9,6 +9,13 @@ enum IntBlock { I_OOOO, I_OVOO, I_OOVO, I_OOOV, I_OVOV, I_OVVO, I_OOVV, I_VOVV, 
 extern const char *const kIntNames[I_COUNT];
 enum InterBlock { X_FAE, X_FMI, X_FME, X_WMNIJ, X_WMBEJ, X_WABEF, X_COUNT };
 
+// Spatial MO integral tensors (aa, bb, ab as transform_to_so takes them; RHF: all three the same tensor): the source
+// any spin-orbital block can be evaluated from without the (2n)^4 tensor (tensor_ops: so_block, so_block_packed)
+struct SoSource {
+    const double *aa = nullptr, *bb = nullptr, *ab = nullptr;
+    int n = 0;
+};
+
 // Pair-packed constants of the symmetric CCSD iteration (ccsd_sym.cu); built once per solve by sym_setup()
 struct SymPack {
     DBuf pairs_buf, ladB, oovvA, tauoP, ovvo_mebj;
@@ -41,11 +48,18 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
                  const double *fvv, const double *D_ijab, int o, int v, double *T2_new,
                  const double *Ts_old = nullptr);
 // ccsd_sym.cu: true if every permutational symmetry the packed formulation relies on holds (checked on the device)
-bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp);
+// I.p[I_VVVV] may be null when `src` is given: <ab||ef> is then checked and pair-packed straight from the spatial tensors
+bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp, const SoSource *src = nullptr);
 void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv, int o, int v,
                         const SymPack &sp, const double *T1, const double *T2, double *T1n, double *T2n);
 void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,
               const double *T2_guess, int o, int v, int maxiter, double conv, double *T1, double *T2, double *e_host,
-              int *iters_host, double *e_hist_host);
+              int *iters_host, double *e_hist_host, const SoSource *src = nullptr);
+// the fused pipeline's front end (mp2.cpp:45-86 + cc.cpp:8-23 without the (2n)^4 tensor): AO->MO, then the ten o/v blocks
+// other than <vv||vv> straight from the spatial tensors, MP2 amplitudes and energy.  `blocks` receives the buffers,
+// `spatial` keeps the MO tensors alive for the CCSD setup (which packs or builds <vv||vv> from them).
+void mp2_blocks_dev(Ctx &ctx, const double *ao, const double *Ca, const double *Cb, const double *ea, const double *eb, int n, int o,
+                    int v, bool uhf, bool want_blocks, DBuf *blocks /*[I_COUNT]*/, IntsDev &I, DBuf spatial[3], SoSource &src,
+                    double *T /*o^2 v^2*/, double *e_host);
 
 }// namespace qcp2

@@ -240,6 +240,111 @@ void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n
     ctx.launched("to_so");
 }
 
+// ---- spin-orbital blocks straight from the spatial MO tensors (never building the (2n)^4 tensor) ----
+// <ij||kl> exactly as integrals.cpp:143-161 writes it (the ten unmatched spin patterns are the zero-initialised ones)
+__device__ __forceinline__ double so_element(const double *__restrict__ aa, const double *__restrict__ bb, const double *__restrict__ ab,
+                                             int n, int i, int j, int k, int l) {
+    const int si = i & 1, sj = j & 1, sk = k & 1, sl = l & 1;
+    const size_t I = i >> 1, J = j >> 1, K = k >> 1, L = l >> 1;
+    const size_t n3 = (size_t) n * n * n, nn = (size_t) n * n;
+    const size_t ikjl = I * n3 + K * nn + J * n + L, jkil = J * n3 + K * nn + I * n + L;
+    if (si == sk && sj == sl) {
+        if (si == sj) {
+            const double *same = si ? bb : aa;
+            return same[ikjl] - same[jkil];// :143-149
+        }
+        return ab[ikjl];                   // :151-155
+    }
+    if (si == sl && sj == sk && si != sj) return -ab[jkil];// :157-161
+    return 0.0;
+}
+// out[p][q][r][s] = <p+m0, q+m1 || r+m2, s+m3>: the slice_ints block (integrals.cpp:184-207) without its source tensor
+__global__ void __launch_bounds__(256) so_block_kernel(const double *__restrict__ aa, const double *__restrict__ bb,
+                                                       const double *__restrict__ ab, int n, int e1, int e2, int e3, int m0, int m1,
+                                                       int m2, int m3, double *__restrict__ out) {
+    const int p = blockIdx.x / e1, q = blockIdx.x - p * e1;
+    double *dst = out + (size_t) blockIdx.x * e2 * e3;
+    const int total = e2 * e3;
+    for (int rs = blockIdx.y * blockDim.x + threadIdx.x; rs < total; rs += gridDim.y * blockDim.x) {
+        const int r = rs / e3, sidx = rs - r * e3;
+        dst[rs] = so_element(aa, bb, ab, n, p + m0, q + m1, r + m2, sidx + m3);
+    }
+}
+void so_block(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec, double *out) {
+    QCP2_REQUIRE(spec && strlen(spec) == 4, "so_block: spec must have 4 characters");
+    int e[4], m[4];
+    for (int d = 0; d < 4; ++d) {
+        QCP2_REQUIRE(spec[d] == 'o' || spec[d] == 'v', "so_block: spec characters must be 'o' or 'v'");
+        e[d] = spec[d] == 'o' ? o : v;
+        m[d] = spec[d] == 'v' ? o : 0;
+    }
+    QCP2_REQUIRE(o + v <= 2 * n, "so_block: o + v exceeds the spin-orbital count");
+    if ((long long) e[0] * e[1] * e[2] * e[3] == 0) return;
+    const long long rows = (long long) e[0] * e[1], panel = (long long) e[2] * e[3];
+    const unsigned ny = (unsigned) std::max<long long>(1, std::min<long long>((panel + 255) / 256, (8LL * ctx.sm_count + rows - 1) / rows));
+    so_block_kernel<<<dim3((unsigned) rows, ny), 256, 0, ctx.stream>>>(aa, bb, ab, n, e[1], e[2], e[3], m[0], m[1], m[2], m[3], out);
+    ctx.launched("so_block");
+}
+// dst[row][q(e<f)] = <p_row + m0, q_row + m1 || e + m2, f + m2> for the (p,q) rows listed in pairs01 (2 ints per row): the
+// pair-packed form of a block (pack_pairs of slice_ints of transform_to_so) without any of the three intermediates
+__global__ void so_block_packed_kernel(const double *__restrict__ aa, const double *__restrict__ bb, const double *__restrict__ ab,
+                                       int n, const int *__restrict__ pairs01, int m0, int m1, int m2, int d23,
+                                       double *__restrict__ dst, long long ld) {
+    const int p = pairs01[2 * blockIdx.x] + m0, q = pairs01[2 * blockIdx.x + 1] + m1;
+    double *d = dst + (size_t) blockIdx.x * (size_t) ld;
+    for (int e = blockIdx.y; e + 1 < d23; e += gridDim.y) {
+        const size_t q0 = (size_t) e * d23 - (size_t) e * (e + 1) / 2 - (e + 1);
+        for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) d[q0 + f] = so_element(aa, bb, ab, n, p, q, e + m2, f + m2);
+    }
+}
+void so_block_packed(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int m0, int m1, int m2, int d23,
+                     const int *pairs01, int n01, double *dst, long long ld) {
+    if (n01 <= 0 || d23 < 2) return;
+    const unsigned ny = n01 >= 8 * ctx.sm_count ? 1u : (unsigned) std::min(d23 - 1, (8 * ctx.sm_count + n01 - 1) / n01);
+    so_block_packed_kernel<<<dim3((unsigned) n01, ny), d23 >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(aa, bb, ab, n, pairs01, m0, m1, m2,
+                                                                                                     d23, dst, ld);
+    ctx.launched("so_block_packed");
+}
+// antisymmetry of the <vv||vv> block in (a,b) and in (e,f), evaluated from the spatial tensors: res[0..1] = max |x + P_ab x|, max |x|,
+// res[2..3] the same for (e,f)  (bit patterns of non-negative doubles, accumulated with atomicMax; zero res first)
+__global__ void so_vvvv_defect_kernel(const double *__restrict__ aa, const double *__restrict__ bb, const double *__restrict__ ab, int n,
+                                      int o, int v, unsigned long long *__restrict__ res) {
+    const long long total = (long long) v * v * v * v;
+    double d0 = 0.0, d1 = 0.0, mx = 0.0;
+    GRID_STRIDE(lin, total) {
+        long long r = lin;
+        const int f = (int) (r % v);
+        r /= v;
+        const int e = (int) (r % v);
+        r /= v;
+        const int b = (int) (r % v);
+        const int a = (int) (r / v);
+        if (a > b || e > f) continue;// every unordered pair of pairs once
+        const double x = so_element(aa, bb, ab, n, a + o, b + o, e + o, f + o);
+        d0 = fmax(d0, fabs(x + so_element(aa, bb, ab, n, b + o, a + o, e + o, f + o)));
+        d1 = fmax(d1, fabs(x + so_element(aa, bb, ab, n, a + o, b + o, f + o, e + o)));
+        mx = fmax(mx, fabs(x));
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        d0 = fmax(d0, __shfl_xor_sync(0xffffffffu, d0, sft));
+        d1 = fmax(d1, __shfl_xor_sync(0xffffffffu, d1, sft));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(res, (unsigned long long) __double_as_longlong(d0));
+        atomicMax(res + 1, (unsigned long long) __double_as_longlong(mx));
+        atomicMax(res + 2, (unsigned long long) __double_as_longlong(d1));
+        atomicMax(res + 3, (unsigned long long) __double_as_longlong(mx));
+    }
+}
+void so_vvvv_defect_async(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, unsigned long long *res) {
+    const long long total = (long long) v * v * v * v;
+    if (total == 0) return;
+    so_vvvv_defect_kernel<<<grid_for(total, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(aa, bb, ab, n, o, v, res);
+    ctx.launched("so_vvvv_defect");
+}
+
 // integrals.cpp:184-207.  blockIdx.x = (p,q) pair of the block's first two indices, blockIdx.y = a
 // chunk of kSliceRows rows r of the (r,s) panel.  A warp copies four rows at a time (four
 // independent loads in flight per lane before the first store), lanes sweep the contiguous s.

@@ -15,6 +15,13 @@ void fill_zero(Ctx &ctx, double *p, long long n);
 // integrals.cpp / mp2.cpp
 void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, double *so);
 void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *spec, double *out);
+// spin-orbital blocks straight from the spatial MO tensors (aa, bb, ab as transform_to_so takes them), bit-identical to
+// slice_ints(transform_to_so(...)) -- the (2n)^4 tensor is never built
+void so_block(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec, double *out);
+// pair-packed rows: dst[row][q(e<f)] = <pairs[2 row] + m0, pairs[2 row + 1] + m1 || e + m2, f + m2>, e < f < d23
+void so_block_packed(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int m0, int m1, int m2, int d23,
+                     const int *pairs01, int n01, double *dst, long long ld);
+void so_vvvv_defect_async(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, unsigned long long *res);
 void make_denom(Ctx &ctx, const double *F_spin, int n2, int o, int v, double *denom);
 void make_so_moes(Ctx &ctx, const double *ea, const double *eb, int n, double *F);
 void mp2_amplitudes_energy(Ctx &ctx, const double *oovv, const double *denom, long long n, double *T, double *e_dev);

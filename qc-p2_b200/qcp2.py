@@ -48,6 +48,7 @@ def load_library():
         lib.qcp2_sharded_gemms.restype = C.c_longlong
         lib.qcp2_gemm_counts.restype = C.c_longlong
         lib.qcp2_gemm_log_read.restype = C.c_longlong
+        lib.qcp2_pool_high_water.restype = C.c_longlong
         _lib = lib
     return _lib
 
@@ -417,6 +418,17 @@ class Context:
                                           C.c_longlong(strideA), C.c_longlong(strideB), C.c_longlong(strideC), int(tile),
                                           int(k_splits), int(reps), C.byref(secs)))
         return secs.value
+
+    def so_block(self, mo_aa, mo_bb, mo_ab, no, nv, int_string):
+        """qcp2_so_block: slice_ints(transform_to_so(..)) gathered straight from the spatial MO tensors."""
+        aa, bb, ab = _arr(mo_aa), _arr(mo_bb), _arr(mo_ab)
+        out = np.empty(int_shape(int_string, no, nv))
+        self.check(self.lib.qcp2_so_block(self.h, _p(aa), _p(bb), _p(ab), aa.shape[0], no, nv, int_string.encode(), _p(out)))
+        return out
+
+    def pool_high_water(self):
+        """Peak bytes of the context's workspace pool since the start of the last post_hf call."""
+        return int(self.lib.qcp2_pool_high_water(self.h))
 
     def gemm_log(self, enable=True):
         self.check(self.lib.qcp2_gemm_log(self.h, int(bool(enable))))

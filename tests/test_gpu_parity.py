@@ -252,6 +252,20 @@ def test_ccsd_from_presliced_blocks_and_maxiter_cap(ctx):
     assert close(res["T2"], r["T2"]) and close(res["T1"], r["T1"])
 
 
+def test_so_block_is_the_slice_of_transform_to_so_bit_for_bit(ctx):
+    """The fused pipeline gathers every o/v block straight from the spatial MO tensors (the (2n)^4 tensor is never built);
+    the values must be the ones integrals.cpp:136-167 + 184-207 produce: RHF-type (aa = bb = ab) and as-written UHF."""
+    rng = np.random.default_rng(5)
+    n, o = 5, 4
+    v = 2 * n - o
+    aa, bb, ab = (rng.standard_normal((n,) * 4) for _ in range(3))
+    for (x, y, z) in ((aa, aa, aa), (aa, bb, ab)):
+        so = npo.transform_to_so(x, y, z)
+        for spec in qcp2_b200.INT_NAMES:
+            got = ctx.so_block(x, y, z, o, v, spec)
+            assert np.array_equal(got, npo.slice_ints(so, o, spec)), spec
+
+
 # ---------------------------------------------------------------------------- (T)
 @pytest.mark.parametrize("o,v", [(3, 4), (4, 6), (4, 7), (5, 17), (6, 33), (3, 39)])  # v(v-1)/2 odd for v = 6, 7; v^2 odd for 7, 17, 33, 39
 def test_t_synthetic_small_all_modes(ctx, o, v):

@@ -240,6 +240,11 @@ long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap
  * the spatial MO tensors (integrals.cpp:136-167 + 184-207 fused; bit-identical values).  out has the block's extents. */
 int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec,
                   double *out);
+/* Formulation the last CCSD solve of this context ran (qcp2_ccsd, qcp2_post_hf*): 0 = the dense term list of cc.cpp (inputs
+ * without the permutational symmetries of RHF-type integrals, e.g. the as-written UHF path), 1 = pair-packed / factorised
+ * (ccsd_sym.cu), 2 = pair-packed with one block per spin class (the inputs carry the zero pattern of transform_to_so,
+ * integrals.cpp:143-161); -1 before the first solve. */
+int qcp2_ccsd_last_mode(const qcp2_ctx *ctx);
 /* High-water mark (bytes) of the context's workspace pool since the start of the last qcp2_post_hf / qcp2_post_hf_mgpu
  * call: the peak device memory the fused pipeline needed (caller-owned device buffers not included); -1 if unknown. */
 long long qcp2_pool_high_water(const qcp2_ctx *ctx);

@@ -1064,6 +1064,8 @@ int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const doubl
     });
 }
 
+int qcp2_ccsd_last_mode(const qcp2_ctx *ctx) { return ctx ? ctx->c.last_ccsd_mode : -1; }
+
 long long qcp2_pool_high_water(const qcp2_ctx *ctx) {
     if (!ctx || !ctx->c.pool) return -1;
     unsigned long long hi = 0;

@@ -38,91 +38,149 @@ TView int_view4(const IntsDev &I, int k, int o, int v) {
 long long even(long long n) { return (n + 1) & ~1LL; }
 }// namespace
 
-bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp, const SoSource *src) {
+bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, const double *fov, int o, int v, SymPack &sp, const SoSource *src) {
     const long long O = o, V = v;
     if (o < 2 || v < 2 || getenv("QCP2_CCSD_DENSE")) return false;
     Trace tr(ctx, "ccsd sym_setup");
-    unsigned long long *chk = static_cast<unsigned long long *>(ctx.alloc_bytes(16 * 12));
-    QCP2_CUDA(cudaMemsetAsync(chk, 0, 16 * 12, ctx.stream));
+    constexpr int kSlots = 48;
+    unsigned long long *chk = static_cast<unsigned long long *>(ctx.alloc_bytes(8 * kSlots));
+    QCP2_CUDA(cudaMemsetAsync(chk, 0, 8 * kSlots, ctx.stream));
+    // ---- permutational symmetries the packed formulation relies on: slots [0, 20), (defect, max) pairs
     int nchk = 0;
     auto check = [&](const double *x, long long d0, long long d1, long long d2, long long d3, int pair) {
         antisymmetry_defect_async(ctx, x, d0, d1, d2, d3, pair, chk + 2 * nchk++);
     };
     const bool direct = I.p[I_VVVV] == nullptr;// <ab||ef> is evaluated from the spatial MO tensors, never stored unpacked
     QCP2_REQUIRE(!direct || (src && src->aa && src->bb && src->ab), "ccsd: <vv||vv> missing and no spatial integrals to build it from");
-    if (direct) so_vvvv_defect_async(ctx, src->aa, src->bb, src->ab, src->n, o, v, chk), nchk = 2;
-    else check(I.p[I_VVVV], V, V, V, V, 0), check(I.p[I_VVVV], V, V, V, V, 1);// <ab||ef>: a<b rows, e<f columns
+    unsigned long long *vv_forbidden = chk + 44;// slots 40..44 belong to the direct <vv||vv> scan
+    if (direct) {
+        so_vvvv_defect_async(ctx, src->aa, src->bb, src->ab, src->n, o, v, chk + 40);
+    } else {
+        check(I.p[I_VVVV], V, V, V, V, 0), check(I.p[I_VVVV], V, V, V, V, 1);// <ab||ef>: a<b rows, e<f columns
+    }
     check(I.p[I_OOVV], O, O, V, V, 0), check(I.p[I_OOVV], O, O, V, V, 1);// <mn||ef>: m<n, e<f
     check(I.p[I_VOVV], V, O, V, V, 1);                                  // <am||ef>: e<f
     check(I.p[I_OOOO], O, O, O, O, 0), check(I.p[I_OOOO], O, O, O, O, 1);// W_mnij: m<n, i<j
     check(I.p[I_OOOV], O, O, O, V, 0);                                  // W_mnij's t.<mn||ie> terms: m<n
     check(T2_guess, O, O, V, V, 0), check(T2_guess, O, O, V, V, 1);     // T2 (hence tau, tau-bar): i<j, a<b
-    unsigned long long h[24];
-    QCP2_CUDA(cudaMemcpyAsync(h, chk, 16 * 12, cudaMemcpyDeviceToHost, ctx.stream));
+    // ---- spin zero pattern (integrals.cpp:143-161): one max|x| over the spin-forbidden elements per tensor, slots [20, 36) + 44
+    int nspin = 0;
+    const bool want_spin = getenv("QCP2_CCSD_NO_SPIN_BLOCKS") == nullptr;
+    if (want_spin) {
+        auto spin = [&](const double *x, const char *spec) {
+            long long d[4];
+            int off[4];
+            for (int k = 0; k < 4; ++k) d[k] = spec[k] == 'o' ? O : V, off[k] = spec[k] == 'o' ? 0 : o;
+            spin_pattern_defect_async(ctx, x, d, off, chk + 20 + nspin++);
+        };
+        for (int k = 0; k < I_COUNT; ++k)
+            if (I.p[k]) spin(I.p[k], kIntNames[k]);
+        spin(T2_guess, "oovv");
+        if (fov) {// s_i != s_a must vanish: the same rule with two unit dimensions of even (alpha) parity
+            const long long d[4] = {1, O, 1, V};
+            const int off[4] = {0, 0, 0, o};
+            spin_pattern_defect_async(ctx, fov, d, off, chk + 20 + nspin++);
+        }
+        QCP2_REQUIRE(nspin <= 16, "sym_setup: spin check slots");
+    }
+    unsigned long long h[kSlots];
+    QCP2_CUDA(cudaMemcpyAsync(h, chk, 8 * kSlots, cudaMemcpyDeviceToHost, ctx.stream));
     ctx.sync();
     ctx.free(chk);
-    for (int q = 0; q < nchk; ++q) {
-        double defect, mx;
-        memcpy(&defect, &h[2 * q], 8), memcpy(&mx, &h[2 * q + 1], 8);
-        if (!(defect <= 1e-10 * mx)) return false;
+    auto as_double = [&](int slot) {
+        double x;
+        memcpy(&x, &h[slot], 8);
+        return x;
+    };
+    for (int q = 0; q < nchk; ++q)
+        if (!(as_double(2 * q) <= 1e-10 * as_double(2 * q + 1))) return false;
+    if (direct && (!(as_double(40) <= 1e-10 * as_double(41)) || !(as_double(42) <= 1e-10 * as_double(43)))) return false;
+    bool blocked = want_spin;
+    for (int q = 0; q < nspin; ++q) blocked = blocked && as_double(20 + q) == 0.0;
+    if (direct) blocked = blocked && as_double((int) (vv_forbidden - chk)) == 0.0;
+    tr.mark("permutational symmetry + spin pattern checks");
+
+    // ---- pair lists per class and the class / position maps of every natural pair index
+    sp.spin_blocked = blocked, sp.ncls = blocked ? 3 : 1;
+    auto cls_of = [&](int gx, int gy) { return blocked ? (gx & 1) + (gy & 1) : 0; };// global spin-orbital indices
+    std::vector<int> lists[3][4];// per class: rows (i<j), cols (a<b), (a,m), ordered (i,n)
+    std::vector<int> rowcls, rowloc, colcls, colloc, amcls, amloc, allcls, allloc;
+    auto add = [&](int c, int which, int x, int y, std::vector<int> &mc, std::vector<int> &ml) {
+        mc.push_back(c), ml.push_back((int) (lists[c][which].size() / 2));
+        lists[c][which].push_back(x), lists[c][which].push_back(y);
+    };
+    for (int i = 0; i < o; ++i)
+        for (int j = i + 1; j < o; ++j) add(cls_of(i, j), 0, i, j, rowcls, rowloc);
+    for (int a = 0; a < v; ++a)
+        for (int b = a + 1; b < v; ++b) add(cls_of(o + a, o + b), 1, a, b, colcls, colloc);
+    for (int a = 0; a < v; ++a)
+        for (int m = 0; m < o; ++m) add(cls_of(o + a, m), 2, a, m, amcls, amloc);
+    for (int i = 0; i < o; ++i)
+        for (int n = 0; n < o; ++n) add(cls_of(i, n), 3, i, n, allcls, allloc);
+    sp.npo = (int) rowcls.size(), sp.npv = (int) colcls.size();
+    std::vector<int> flat;
+    size_t list_off[3][4], map_off[8];
+    for (int c = 0; c < sp.ncls; ++c)
+        for (int w = 0; w < 4; ++w) list_off[c][w] = flat.size(), flat.insert(flat.end(), lists[c][w].begin(), lists[c][w].end());
+    const std::vector<int> *maps[8] = {&rowcls, &rowloc, &colcls, &colloc, &amcls, &amloc, &allcls, &allloc};
+    for (int k = 0; k < 8; ++k) map_off[k] = flat.size(), flat.insert(flat.end(), maps[k]->begin(), maps[k]->end());
+    sp.ints_buf = DBuf(ctx, (flat.size() * sizeof(int) + 7) / 8 + 1);
+    int *pd = reinterpret_cast<int *>(sp.ints_buf.p);
+    QCP2_CUDA(cudaMemcpyAsync(pd, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
+    ctx.sync();// flat is pageable
+    if (blocked) {
+        sp.rowcls = pd + map_off[0], sp.rowloc = pd + map_off[1], sp.colcls = pd + map_off[2], sp.colloc = pd + map_off[3];
+        sp.amcls = pd + map_off[4], sp.amloc = pd + map_off[5], sp.allcls = pd + map_off[6], sp.allloc = pd + map_off[7];
     }
-    tr.mark("permutational symmetry checks");
-    // pair lists: i<j | a<b | all (a,m) | all (i,n)
-    std::vector<int> pr;
-    for (int i = 0; i < o; ++i)
-        for (int j = i + 1; j < o; ++j) pr.push_back(i), pr.push_back(j);
-    const size_t n_po = pr.size();
-    for (int a = 0; a < v; ++a)
-        for (int b = a + 1; b < v; ++b) pr.push_back(a), pr.push_back(b);
-    const size_t n_pv = pr.size();
-    for (int a = 0; a < v; ++a)
-        for (int m = 0; m < o; ++m) pr.push_back(a), pr.push_back(m);
-    const size_t n_am = pr.size();
-    for (int i = 0; i < o; ++i)
-        for (int n = 0; n < o; ++n) pr.push_back(i), pr.push_back(n);
-    sp.pairs_buf = DBuf(ctx, (pr.size() * sizeof(int) + 7) / 8);
-    int *pd = reinterpret_cast<int *>(sp.pairs_buf.p);
-    QCP2_CUDA(cudaMemcpyAsync(pd, pr.data(), pr.size() * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
-    ctx.sync();// pr is pageable
-    sp.pairs_o = pd, sp.pairs_all = pd + n_am;
-    sp.npo = (int) (n_po / 2), sp.npv = (int) ((n_pv - n_po) / 2);
-    sp.ld = even(sp.npv), sp.ldo = even(sp.npo);
-    // row-concatenated right operand of the tau product: <ab||ef> | <am||ef> | <mn||ef>, each segment starting on an even
-    // row so that the matching column segments of the result stay 16-byte aligned
-    sp.offZ = even(sp.npv), sp.offY = sp.offZ + even(V * O), sp.ntot = sp.offY + sp.npo, sp.ldl = even(sp.ntot);
-    sp.ladB = DBuf(ctx, (size_t) (sp.ntot * sp.ld));
-    QCP2_CUDA(cudaMemsetAsync(sp.ladB.p, 0, (size_t) (sp.ntot * sp.ld) * 8, ctx.stream));
-    if (direct) so_block_packed(ctx, src->aa, src->bb, src->ab, src->n, o, o, o, v, pd + n_po, sp.npv, sp.ladB.p, sp.ld);
-    else pack_pairs(ctx, I.p[I_VVVV], v, v, pd + n_po, sp.npv, sp.ladB.p, sp.ld);
-    pack_pairs(ctx, I.p[I_VOVV], o, v, pd + n_pv, (int) (V * O), sp.ladB.p + sp.offZ * sp.ld, sp.ld);// row (a,m) = a*o + m
-    pack_pairs(ctx, I.p[I_OOVV], o, v, pd, sp.npo, sp.ladB.p + sp.offY * sp.ld, sp.ld);
-    sp.oovvA = DBuf(ctx, (size_t) (O * O * sp.ld));
-    pack_pairs(ctx, I.p[I_OOVV], o, v, sp.pairs_all, (int) (O * O), sp.oovvA.p, sp.ld);
-    sp.tauoP = DBuf(ctx, (size_t) (sp.npo * sp.ld));
+    // ---- per class: the row-concatenated right operand of the tau product, <ab||ef> | <am||ef> | <mn||ef> (each segment
+    // starting on an even row, so the matching column segments of the result stay 16-byte aligned), all on e<f of the class
+    for (int c = 0; c < sp.ncls; ++c) {
+        SymPack::Cls &k = sp.cls[c];
+        k.nrow = (int) (lists[c][0].size() / 2), k.ncol = (int) (lists[c][1].size() / 2), k.nam = (int) (lists[c][2].size() / 2),
+        k.nall = (int) (lists[c][3].size() / 2);
+        k.rows = pd + list_off[c][0], k.cols = pd + list_off[c][1], k.ams = pd + list_off[c][2], k.alls = pd + list_off[c][3];
+        k.ldk = even(std::max(k.ncol, 1)), k.ldo = even(std::max(k.nrow, 1)), k.lda = even(std::max(k.nall, 1));
+        k.offZ = even(k.ncol), k.offY = k.offZ + even(k.nam), k.ntot = k.offY + k.nrow, k.ldl = even(std::max<long long>(k.ntot, 1));
+        if (k.ncol == 0) continue;
+        PairColMap cm;
+        cm.cls = sp.colcls, cm.loc = sp.colloc, cm.want = c;
+        k.ladB = DBuf(ctx, (size_t) (std::max<long long>(k.ntot, 1) * k.ldk));
+        QCP2_CUDA(cudaMemsetAsync(k.ladB.p, 0, (size_t) (std::max<long long>(k.ntot, 1) * k.ldk) * 8, ctx.stream));
+        if (direct) so_block_packed(ctx, src->aa, src->bb, src->ab, src->n, o, o, o, v, k.cols, k.ncol, k.ladB.p, k.ldk, cm);
+        else pack_pairs(ctx, I.p[I_VVVV], v, v, k.cols, k.ncol, k.ladB.p, k.ldk, cm);
+        pack_pairs(ctx, I.p[I_VOVV], o, v, k.ams, k.nam, k.ladB.p + k.offZ * k.ldk, k.ldk, cm);// source row (a,m) = a*o + m
+        pack_pairs(ctx, I.p[I_OOVV], o, v, k.rows, k.nrow, k.ladB.p + k.offY * k.ldk, k.ldk, cm);
+        k.oovvA = DBuf(ctx, (size_t) (std::max(k.nall, 1) * k.ldk));
+        pack_pairs(ctx, I.p[I_OOVV], o, v, k.alls, k.nall, k.oovvA.p, k.ldk, cm);
+        k.tauoP = DBuf(ctx, (size_t) (std::max(k.nrow, 1) * k.ldk));
+    }
     sp.ovvo_mebj = DBuf(ctx, (size_t) (O * V * V * O));
     {
         const long long ext[4] = {O, V, V, O}, istr[4] = {V * V * O, O, V * O, 1};// <mb||ej> read as [m,e,b,j]
         permute_axpby(ctx, sp.ovvo_mebj.p, I.p[I_OVVO], 4, ext, istr, 1.0, 0.0);
     }
-    tr.mark("pack <vv||vv>, <vo||vv>, <oo||vv> to pairs");
+    tr.mark(blocked ? "pack <vv||vv>, <vo||vv>, <oo||vv> to pairs, one block per spin class" : "pack <vv||vv>, <vo||vv>, <oo||vv> to pairs");
     return true;
 }
 
 void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv, int o, int v,
                         const SymPack &sp, const double *T1, const double *T2, double *T1n, double *T2n) {
-    const long long O = o, V = v, o2v2 = O * O * V * V, ld = sp.ld, ldo = sp.ldo, ldl = sp.ldl;
-    const int npo = sp.npo, npv = sp.npv;
+    const long long O = o, V = v, o2v2 = O * O * V * V;
+    auto colmap = [&](int c) {
+        PairColMap m;
+        m.cls = sp.colcls, m.loc = sp.colloc, m.want = c;
+        return m;
+    };
     const TView ts(T1, {O, V}), td(T2, {O, O, V, V}), tn(T1n, {O, V});
     const TView oooo = int_view4(I, I_OOOO, o, v), ooov = int_view4(I, I_OOOV, o, v), oovv = int_view4(I, I_OOVV, o, v),
                 ovvv = int_view4(I, I_OVVV, o, v), ovov = int_view4(I, I_OVOV, o, v), oovo = int_view4(I, I_OOVO, o, v),
                 vvvo = int_view4(I, I_VVVO, o, v), ovoo = int_view4(I, I_OVOO, o, v);
-    const double *oovvP = sp.ladB.p + sp.offY * ld;
 
     // ---------------------------------------------------------------- amplitude-derived operands of this iteration
-    DBuf taub(ctx, (size_t) o2v2), taubA(ctx, (size_t) (O * O * ld)), tt(ctx, (size_t) o2v2), lf(ctx, (size_t) o2v2);
+    DBuf taub(ctx, (size_t) o2v2), tt(ctx, (size_t) o2v2), lf(ctx, (size_t) o2v2);
     make_tau(ctx, T1, T2, o, v, true, taub);                                  // tau-bar, dense (F_ae)
-    tau_pack(ctx, T1, T2, o, v, sp.pairs_o, npo, sp.tauoP, ld);               // tau(T1 old, T2), i<j, a<b
-    tau_pack(ctx, T1, T2, o, v, sp.pairs_all, (int) (O * O), taubA, ld, true);// tau-bar, all (i,n), e<f (F_mi)
+    for (int c = 0; c < sp.ncls; ++c)                                         // tau(T1 old, T2) on i<j, a<b, one block per class
+        if (sp.cls[c].nrow && sp.cls[c].ncol) tau_pack(ctx, T1, T2, o, v, sp.cls[c].rows, sp.cls[c].nrow, sp.cls[c].tauoP, sp.cls[c].ldk, false, colmap(c));
     wmbej_amplitudes(ctx, nullptr, T2, o, v, tt);                             // -1/2 t_jnfb as [j,b,n,f]
     {
         const long long ext[4] = {O, V, O, V}, istr[4] = {O * V * V, V, V * V, 1};// t[i,m,a,e] read as [i,a,m,e]
@@ -144,13 +202,18 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     fill_zero(ctx, fmi.p, O * O);
     if (fov) contract(ctx, 0.5, ts, "ie", TView(fov, {O, V}), "me", 1.0, Fmi, "mi");           // :207
     contract(ctx, 1.0, ts, "ne", ooov, "mnie", 1.0, Fmi, "mi");                                // :208
-    {// :209  1/2 sum_{n,ef} taub_inef <mn||ef> = sum_n sum_{e<f}: the n = n' trace of [(i,n)] x [(m,n')] on e<f pairs
-        DBuf gg(ctx, (size_t) (O * O * even(O * O)));
+    for (int c = 0; c < sp.ncls; ++c) {// :209  1/2 sum_{n,ef} taub_inef <mn||ef> = sum_n sum_{e<f}: the n = n' trace of [(i,n)] x [(m,n')]
+        const SymPack::Cls &k = sp.cls[c];
+        if (!k.nall || !k.ncol) continue;
+        DBuf taubA(ctx, (size_t) (k.nall * k.ldk)), gg(ctx, (size_t) (k.nall * k.lda));
+        tau_pack(ctx, T1, T2, o, v, k.alls, k.nall, taubA, k.ldk, true, colmap(c));// tau-bar, ordered (i,n) pairs, e<f
         GemmArgs g;
-        g.M = (int) (O * O), g.N = (int) (O * O), g.K = npv;
-        g.A = taubA, g.lda = ld, g.B = sp.oovvA, g.ldb = ld, g.C = gg, g.ldc = even(O * O);
+        g.M = k.nall, g.N = k.nall, g.K = k.ncol;
+        g.A = taubA, g.lda = k.ldk, g.B = k.oovvA, g.ldb = k.ldk, g.C = gg, g.ldc = k.lda;
         gemm(ctx, g, true, false);
-        pair_trace_add(ctx, gg, even(O * O), o, fmi.p);
+        PairColMap all;
+        all.cls = sp.allcls, all.loc = sp.allloc, all.want = c;
+        pair_trace_add(ctx, gg, k.lda, o, all, fmi.p);
     }
     add_offdiag(ctx, fmi.p, foo, o);                                                          // :212-216
 
@@ -159,13 +222,15 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
 
     contract(ctx, 1.0, ts, "je", ooov, "mnie", 1.0, Wmnij, "mnij", oooo.p);                    // :229 + :232
     contract(ctx, -1.0, ts, "ie", ooov, "mnje", 1.0, Wmnij, "mnij");                           // :230
-    {// :231  1/4 tau_ijef <mn||ef> = 1/2 sum_{e<f} on [i<j][m<n], unpacked with both signs
-        DBuf yo(ctx, (size_t) (npo * ldo));
+    for (int c = 0; c < sp.ncls; ++c) {// :231  1/4 tau_ijef <mn||ef> = 1/2 sum_{e<f} on [i<j][m<n], unpacked with both signs
+        const SymPack::Cls &k = sp.cls[c];
+        if (!k.nrow || !k.ncol) continue;
+        DBuf yo(ctx, (size_t) (k.nrow * k.ldo));
         GemmArgs g;
-        g.M = npo, g.N = npo, g.K = npv;
-        g.A = sp.tauoP, g.lda = ld, g.B = oovvP, g.ldb = ld, g.C = yo, g.ldc = ldo;
+        g.M = k.nrow, g.N = k.nrow, g.K = k.ncol;
+        g.A = k.tauoP, g.lda = k.ldk, g.B = k.ladB.p + k.offY * k.ldk, g.ldb = k.ldk, g.C = yo, g.ldc = k.ldo;
         gemm(ctx, g, true, false);
-        wmnij_unpack_add(ctx, yo, ldo, o, 0.5, wmnij.p);
+        wmnij_unpack_add(ctx, yo, k.ldo, o, k.rows, k.nrow, 0.5, wmnij.p);
     }
     {// W_mbej as [m,e,b,j]
         contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 1.0, Wm, "mebj", sp.ovvo_mebj.p);           // :245 + :250
@@ -205,37 +270,43 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     contract(ctx, -1.0, td, "imab", D2, "mj", 0.0, Uij, "ijab");                               // :333 + :340
     contract(ctx, 1.0, tn, "ie", vvvo, "abej", 1.0, Uij, "ijab");                              // :366
 
-    // everything that multiplies tau = tau(new T1, T2), on [i<j] rows:
+    // everything that multiplies tau = tau(new T1, T2), on [i<j] rows, one block per class:
     //   [ LP | Z | Y ] = tauP . [ <ab||ef> ; <am||ef> ; <mn||ef> ]^T      (sums over e<f carry the factor 2)
     //   LP += 1/2 Y . tau_oldP                1/8 tau <mn||ef> tau_old     (cc.cpp:239 inside :348)
     //   LP += W_mnijP . tauP                  1/2 tau_mnab W_mnij          (cc.cpp:346)
     //   LP -= P(ab) Z . t_old                 -1/2 P(ab) tau <am||ef> t    (cc.cpp:237-238 inside :348)
-    DBuf tauP(ctx, (size_t) (npo * ld)), lpz(ctx, (size_t) (npo * ldl)), wp(ctx, (size_t) (npo * ldo)), xab(ctx, (size_t) (npo * V * V));
-    tau_pack(ctx, T1n, T2, o, v, sp.pairs_o, npo, tauP, ld);
-    {
+    DBuf lpz[3];
+    LadderBlocks lb;
+    lb.rowcls = sp.rowcls, lb.rowloc = sp.rowloc, lb.colcls = sp.colcls, lb.colloc = sp.colloc;
+    for (int c = 0; c < sp.ncls; ++c) {
+        const SymPack::Cls &k = sp.cls[c];
+        lpz[c] = DBuf(ctx, (size_t) (std::max(k.nrow, 1) * k.ldl));
+        lb.lp[c] = lpz[c].p, lb.ld[c] = k.ldl;
+        if (!k.nrow || !k.ncol) {
+            if (k.nrow) fill_zero(ctx, lpz[c].p, k.nrow * k.ldl);
+            continue;
+        }
+        DBuf tauP(ctx, (size_t) (k.nrow * k.ldk)), wp(ctx, (size_t) (k.nrow * k.ldo));
+        tau_pack(ctx, T1n, T2, o, v, k.rows, k.nrow, tauP, k.ldk, false, colmap(c));
         GemmArgs g;
-        g.M = npo, g.N = (int) sp.ntot, g.K = npv;
-        g.A = tauP, g.lda = ld;       // [M][K]
-        g.B = sp.ladB, g.ldb = ld;    // [N][K]
-        g.C = lpz, g.ldc = ldl, g.c_owns_rows = true;
+        g.M = k.nrow, g.N = (int) k.ntot, g.K = k.ncol;
+        g.A = tauP, g.lda = k.ldk;       // [M][K]
+        g.B = k.ladB, g.ldb = k.ldk;     // [N][K]
+        g.C = lpz[c], g.ldc = k.ldl, g.c_owns_rows = true;
         gemm(ctx, g, true, false);
-        double *LP = lpz.p, *Z = lpz.p + sp.offZ, *Y = lpz.p + sp.offY;
+        double *LP = lpz[c].p, *Z = lpz[c].p + k.offZ, *Y = lpz[c].p + k.offY;
         GemmArgs g2;
-        g2.M = npo, g2.N = npv, g2.K = npo, g2.alpha = 0.5, g2.beta = 1.0;
-        g2.A = Y, g2.lda = ldl;           // [M][K]
-        g2.B = sp.tauoP, g2.ldb = ld;     // [K][N]
-        g2.C = LP, g2.ldc = ldl;
+        g2.M = k.nrow, g2.N = k.ncol, g2.K = k.nrow, g2.alpha = 0.5, g2.beta = 1.0;
+        g2.A = Y, g2.lda = k.ldl;            // [M][K]
+        g2.B = k.tauoP, g2.ldb = k.ldk;      // [K][N]
+        g2.C = LP, g2.ldc = k.ldl;
         gemm(ctx, g2, true, true);
-        wmnij_pack(ctx, wmnij.p, o, sp.pairs_o, npo, wp, ldo);
-        g2.alpha = 1.0, g2.A = wp, g2.lda = ldo, g2.B = tauP;
+        wmnij_pack(ctx, wmnij.p, o, k.rows, k.nrow, wp, k.ldo);
+        g2.alpha = 1.0, g2.A = wp, g2.lda = k.ldo, g2.B = tauP;
         gemm(ctx, g2, true, true);
-        GemmArgs gx;// X[p][a][b] = sum_m Z[p][a,m] t_old[m,b], one batch member per pair p
-        gx.M = v, gx.N = v, gx.K = o, gx.batch = npo;
-        gx.A = Z, gx.lda = O, gx.strideA = ldl;
-        gx.B = T1, gx.ldb = V, gx.strideB = 0;
-        gx.C = xab, gx.ldc = V, gx.strideC = V * V;
-        gemm(ctx, gx, true, true);
-        packed_antisym_sub(ctx, xab, npo, v, LP, ldl);
+        PairColMap am;
+        am.cls = sp.amcls, am.loc = sp.amloc, am.want = c;
+        z_t_sub(ctx, Z, k.ldl, T1, o, v, k.nrow, LP, k.ldl, colmap(c), am);
     }
     // ring terms cc.cpp:354-363: Rt[i,a,b,j] = sum_me t_imae W_mbej + sum_m t_ma (sum_e t_ie <mb||je>), used at four relabelings
     DBuf rt(ctx, (size_t) o2v2), p1(ctx, (size_t) (O * O * V * O));
@@ -243,7 +314,7 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     contract(ctx, 1.0, tn, "ie", ovov, "mbje", 0.0, P1, "imbj");
     contract(ctx, 1.0, tn, "ma", P1, "imbj", 0.0, Rt, "iabj");                                 // :360-363 (first writer)
     contract(ctx, 1.0, Lf, "iame", Wm, "mebj", 1.0, Rt, "iabj");                               // :354-357
-    finalize_t2(ctx, I.p[I_OOVV], uab, uij, rt, lpz, ldl, foo, fvv, nullptr, o, v, T2n);       // :312, P(..) combines, :374-383
+    finalize_t2(ctx, I.p[I_OOVV], uab, uij, rt, lb, foo, fvv, nullptr, o, v, T2n);             // :312, P(..) combines, :374-383
 }
 
 }// namespace qcp2

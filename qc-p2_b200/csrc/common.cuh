@@ -58,6 +58,7 @@ struct Ctx {
     long long launches = 0;
     std::string last_error;
     double ccsd_loop_seconds = 0.0;
+    int last_ccsd_mode = -1;// formulation the last CCSD solve used: 0 dense term list, 1 pair-packed, 2 pair-packed + spin classes
     PermCache *perm_cache = nullptr;
     // row-sharded GEMMs (dgemm.cu): while set, every product above shard_min_flops whose result is a dense row-major
     // matrix is split by rows over the communicator's ranks and re-assembled with one broadcast per rank

@@ -331,8 +331,10 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
     // antisymmetry, SURVEY.md Q5 -- keeps the dense term list below.
     Trace tr(ctx, "ccsd_dev");
     SymPack sp;
-    const bool sym = sym_setup(ctx, I, T2_guess, o, v, sp, src);
-    tr.mark(sym ? "symmetric formulation: checks + packing" : "dense formulation (symmetry checks)");
+    const bool sym = sym_setup(ctx, I, T2_guess, fov, o, v, sp, src);
+    tr.mark(sym ? (sp.spin_blocked ? "symmetric formulation, spin-blocked pairs: checks + packing" : "symmetric formulation: checks + packing")
+                : "dense formulation (symmetry checks)");
+    ctx.last_ccsd_mode = sym ? (sp.spin_blocked ? 2 : 1) : 0;
     DBuf vvvv_own;
     if (!sym && I.p[I_VVVV] == nullptr) {// the dense term list reads the v^4 block itself
         QCP2_REQUIRE(src && src->aa, "ccsd: <vv||vv> missing and no spatial integrals to build it from");

@@ -16,14 +16,27 @@ struct SoSource {
     int n = 0;
 };
 
-// Pair-packed constants of the symmetric CCSD iteration (ccsd_sym.cu); built once per solve by sym_setup()
+// Pair-packed constants of the symmetric CCSD iteration (ccsd_sym.cu); built once per solve by sym_setup().
+// Pairs are grouped into CLASSES.  Without spin structure there is one class.  When the inputs carry the spin zero
+// pattern of transform_to_so (integrals.cpp:143-161: <pq||rs> = 0 unless s_p + s_q = s_r + s_s; checked on the device,
+// exact zeros) a pair (x,y) belongs to class s_x + s_y (0 = alpha-alpha, 1 = mixed, 2 = beta-beta) and every pair-packed
+// matrix is block diagonal in the class: only the diagonal blocks are stored and multiplied.
 struct SymPack {
-    DBuf pairs_buf, ladB, oovvA, tauoP, ovvo_mebj;
-    const int *pairs_o = nullptr;   // i<j pairs (2 ints each)
-    const int *pairs_all = nullptr; // all (i,n) pairs
+    DBuf ints_buf, ovvo_mebj;
+    int ncls = 1;
+    bool spin_blocked = false;
     int npo = 0, npv = 0;
-    long long ld = 0, ldo = 0;      // row strides of [..][a<b] and [..][i<j] matrices (even)
-    long long offZ = 0, offY = 0, ntot = 0, ldl = 0;// row segments of ladB = column segments of tauP . ladB^T
+    struct Cls {
+        int nrow = 0, ncol = 0, nam = 0, nall = 0;// i<j pairs, a<b pairs, (a,m) pairs, ordered (i,n) pairs of the class
+        long long ldk = 0;                        // row stride of the [..][a<b] matrices of the class (even)
+        long long ldo = 0, lda = 0;               // row strides of [..][i<j] and [..][(i,n)] matrices
+        long long offZ = 0, offY = 0, ntot = 0, ldl = 0;// row segments of ladB = column segments of tauP . ladB^T
+        const int *rows = nullptr, *cols = nullptr, *ams = nullptr, *alls = nullptr;// device pair lists (2 ints per pair)
+        DBuf ladB, oovvA, tauoP;                  // [<ab||ef>; <am||ef>; <mn||ef>][e<f], <(m,n)||ef> all ordered pairs, tau(T1 old, T2)
+    } cls[3];
+    // class / position of every natural pair index (null when ncls == 1: natural order)
+    const int *rowcls = nullptr, *rowloc = nullptr, *colcls = nullptr, *colloc = nullptr, *amcls = nullptr, *amloc = nullptr,
+              *allcls = nullptr, *allloc = nullptr;
 };
 
 struct IntsDev {
@@ -49,7 +62,8 @@ void make_T2_dev(Ctx &ctx, const double *Ts, const double *Td, const IntsDev &I,
                  const double *Ts_old = nullptr);
 // ccsd_sym.cu: true if every permutational symmetry the packed formulation relies on holds (checked on the device)
 // I.p[I_VVVV] may be null when `src` is given: <ab||ef> is then checked and pair-packed straight from the spatial tensors
-bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, int o, int v, SymPack &sp, const SoSource *src = nullptr);
+bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, const double *fov, int o, int v, SymPack &sp,
+               const SoSource *src = nullptr);
 void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv, int o, int v,
                         const SymPack &sp, const double *T1, const double *T2, double *T1n, double *T2n);
 void ccsd_dev(Ctx &ctx, const IntsDev &I, const double *foo, const double *fov, const double *fvv,

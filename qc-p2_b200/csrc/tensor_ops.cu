@@ -240,6 +240,18 @@ void to_so(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n
     ctx.launched("to_so");
 }
 
+// Column maps of the pair-packed matrices: the natural pair index q(e<f) belongs to class cm.cls[q] and sits at column
+// cm.loc[q] of that class's block; a kernel working on class cm.want touches only the pairs of that class.
+// Null maps: one class, natural order.
+__device__ __forceinline__ bool pair_col(const PairColMap &m, size_t q, long long &col) {
+    if (!m.cls) {
+        col = (long long) q;
+        return true;
+    }
+    if (m.cls[q] != m.want) return false;
+    col = m.loc[q];
+    return true;
+}
 // ---- spin-orbital blocks straight from the spatial MO tensors (never building the (2n)^4 tensor) ----
 // <ij||kl> exactly as integrals.cpp:143-161 writes it (the ten unmatched spin patterns are the zero-initialised ones)
 __device__ __forceinline__ double so_element(const double *__restrict__ aa, const double *__restrict__ bb, const double *__restrict__ ab,
@@ -289,20 +301,23 @@ void so_block(Ctx &ctx, const double *aa, const double *bb, const double *ab, in
 // pair-packed form of a block (pack_pairs of slice_ints of transform_to_so) without any of the three intermediates
 __global__ void so_block_packed_kernel(const double *__restrict__ aa, const double *__restrict__ bb, const double *__restrict__ ab,
                                        int n, const int *__restrict__ pairs01, int m0, int m1, int m2, int d23,
-                                       double *__restrict__ dst, long long ld) {
+                                       double *__restrict__ dst, long long ld, PairColMap cm) {
     const int p = pairs01[2 * blockIdx.x] + m0, q = pairs01[2 * blockIdx.x + 1] + m1;
     double *d = dst + (size_t) blockIdx.x * (size_t) ld;
     for (int e = blockIdx.y; e + 1 < d23; e += gridDim.y) {
         const size_t q0 = (size_t) e * d23 - (size_t) e * (e + 1) / 2 - (e + 1);
-        for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) d[q0 + f] = so_element(aa, bb, ab, n, p, q, e + m2, f + m2);
+        for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) {
+            long long col;
+            if (pair_col(cm, q0 + f, col)) d[col] = so_element(aa, bb, ab, n, p, q, e + m2, f + m2);
+        }
     }
 }
 void so_block_packed(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int m0, int m1, int m2, int d23,
-                     const int *pairs01, int n01, double *dst, long long ld) {
+                     const int *pairs01, int n01, double *dst, long long ld, PairColMap cm) {
     if (n01 <= 0 || d23 < 2) return;
     const unsigned ny = n01 >= 8 * ctx.sm_count ? 1u : (unsigned) std::min(d23 - 1, (8 * ctx.sm_count + n01 - 1) / n01);
     so_block_packed_kernel<<<dim3((unsigned) n01, ny), d23 >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(aa, bb, ab, n, pairs01, m0, m1, m2,
-                                                                                                     d23, dst, ld);
+                                                                                                     d23, dst, ld, cm);
     ctx.launched("so_block_packed");
 }
 // antisymmetry of the <vv||vv> block in (a,b) and in (e,f), evaluated from the spatial tensors: res[0..1] = max |x + P_ab x|, max |x|,
@@ -310,7 +325,7 @@ void so_block_packed(Ctx &ctx, const double *aa, const double *bb, const double 
 __global__ void so_vvvv_defect_kernel(const double *__restrict__ aa, const double *__restrict__ bb, const double *__restrict__ ab, int n,
                                       int o, int v, unsigned long long *__restrict__ res) {
     const long long total = (long long) v * v * v * v;
-    double d0 = 0.0, d1 = 0.0, mx = 0.0;
+    double d0 = 0.0, d1 = 0.0, mx = 0.0, forb = 0.0;
     GRID_STRIDE(lin, total) {
         long long r = lin;
         const int f = (int) (r % v);
@@ -324,9 +339,11 @@ __global__ void so_vvvv_defect_kernel(const double *__restrict__ aa, const doubl
         d0 = fmax(d0, fabs(x + so_element(aa, bb, ab, n, b + o, a + o, e + o, f + o)));
         d1 = fmax(d1, fabs(x + so_element(aa, bb, ab, n, a + o, b + o, f + o, e + o)));
         mx = fmax(mx, fabs(x));
+        if ((((a + o) & 1) + ((b + o) & 1)) != (((e + o) & 1) + ((f + o) & 1))) forb = fmax(forb, fabs(x));
     }
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) {
+        forb = fmax(forb, __shfl_xor_sync(0xffffffffu, forb, sft));
         d0 = fmax(d0, __shfl_xor_sync(0xffffffffu, d0, sft));
         d1 = fmax(d1, __shfl_xor_sync(0xffffffffu, d1, sft));
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
@@ -336,8 +353,36 @@ __global__ void so_vvvv_defect_kernel(const double *__restrict__ aa, const doubl
         atomicMax(res + 1, (unsigned long long) __double_as_longlong(mx));
         atomicMax(res + 2, (unsigned long long) __double_as_longlong(d1));
         atomicMax(res + 3, (unsigned long long) __double_as_longlong(mx));
+        atomicMax(res + 4, (unsigned long long) __double_as_longlong(forb));
     }
 }
+// max |x| over the elements of a 4-index block whose spins do not conserve (s0 + s1 != s2 + s3; spin of index k of
+// dimension d = (k + off[d]) & 1: even = alpha, odd = beta, integrals.cpp:143-161) -> res[0] (atomicMax of the bit pattern)
+__global__ void spin_pattern_kernel(const double *__restrict__ x, long long d0, long long d1, long long d2, long long d3, int f0, int f1,
+                                    int f2, int f3, unsigned long long *__restrict__ res) {
+    const long long n = d0 * d1 * d2 * d3;
+    double mx = 0.0;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        const int i3 = (int) (r % d3);
+        r /= d3;
+        const int i2 = (int) (r % d2);
+        r /= d2;
+        const int i1 = (int) (r % d1);
+        const int i0 = (int) (r / d1);
+        if ((((i0 + f0) & 1) + ((i1 + f1) & 1)) != (((i2 + f2) & 1) + ((i3 + f3) & 1))) mx = fmax(mx, fabs(x[lin]));
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+    if ((threadIdx.x & 31) == 0) atomicMax(res, (unsigned long long) __double_as_longlong(mx));
+}
+void spin_pattern_defect_async(Ctx &ctx, const double *x, const long long d[4], const int off[4], unsigned long long *res) {
+    const long long n = d[0] * d[1] * d[2] * d[3];
+    if (n == 0) return;
+    spin_pattern_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(x, d[0], d[1], d[2], d[3], off[0], off[1], off[2], off[3], res);
+    ctx.launched("spin_pattern");
+}
+
 void so_vvvv_defect_async(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, unsigned long long *res) {
     const long long total = (long long) v * v * v * v;
     if (total == 0) return;
@@ -739,25 +784,28 @@ void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out) {
 }
 
 __global__ void pack_pairs_kernel(const double *__restrict__ src, int d01, int d23, const int *__restrict__ pairs01,
-                                  double *__restrict__ dst, long long ld) {
+                                  double *__restrict__ dst, long long ld, PairColMap cm) {
     const int a = pairs01[2 * blockIdx.x], b = pairs01[2 * blockIdx.x + 1];
     const double *s = src + ((size_t) a * d01 + b) * d23 * d23;
     double *d = dst + (size_t) blockIdx.x * (size_t) ld;
     for (int e = blockIdx.y; e + 1 < d23; e += gridDim.y) {// blockIdx.y strides the rows so few pairs still fill the GPU
         const size_t q0 = (size_t) e * d23 - (size_t) e * (e + 1) / 2 - (e + 1);// q(e,f) = q0 + f
-        for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) d[q0 + f] = s[(size_t) e * d23 + f];
+        for (int f = e + 1 + threadIdx.x; f < d23; f += blockDim.x) {
+            long long col;
+            if (pair_col(cm, q0 + f, col)) d[col] = s[(size_t) e * d23 + f];
+        }
     }
 }
-void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld) {
+void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld, PairColMap cm) {
     if (n01 <= 0 || d23 < 2) return;
     const unsigned ny = n01 >= 8 * ctx.sm_count ? 1u : (unsigned) std::min(d23 - 1, (8 * ctx.sm_count + n01 - 1) / n01);
-    pack_pairs_kernel<<<dim3((unsigned) n01, ny), d23 >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(src, d01, d23, pairs01, dst, ld);
+    pack_pairs_kernel<<<dim3((unsigned) n01, ny), d23 >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(src, d01, d23, pairs01, dst, ld, cm);
     ctx.launched("pack_pairs");
 }
 
 // dst[p(i<j)][q(a<b)] = Td[i,j,a,b] + t_ia t_jb - t_ib t_ja (Stanton eq. 9 on the packed pairs only)
 __global__ void tau_pack_kernel(const double *__restrict__ ts, const double *__restrict__ td, int o, int v,
-                                const int *__restrict__ pairs_o, double *__restrict__ dst, long long ld, double f) {
+                                const int *__restrict__ pairs_o, double *__restrict__ dst, long long ld, double f, PairColMap cm) {
     const int i = pairs_o[2 * blockIdx.x], j = pairs_o[2 * blockIdx.x + 1];
     const double *s = td + ((size_t) i * o + j) * v * v;
     const double *ti = ts + (size_t) i * v, *tj = ts + (size_t) j * v;
@@ -765,38 +813,45 @@ __global__ void tau_pack_kernel(const double *__restrict__ ts, const double *__r
     for (int a = blockIdx.y; a + 1 < v; a += gridDim.y) {
         const size_t q0 = (size_t) a * v - (size_t) a * (a + 1) / 2 - (a + 1);
         const double tia = f * ti[a], tja = f * tj[a];
-        for (int b = a + 1 + threadIdx.x; b < v; b += blockDim.x) d[q0 + b] = s[(size_t) a * v + b] + tia * tj[b] - ti[b] * tja;
+        for (int b = a + 1 + threadIdx.x; b < v; b += blockDim.x) {
+            long long col;
+            if (pair_col(cm, q0 + b, col)) d[col] = s[(size_t) a * v + b] + tia * tj[b] - ti[b] * tja;
+        }
     }
 }
 void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,
-              bool bar) {
+              bool bar, PairColMap cm) {
     if (npo <= 0 || v < 2) return;
     const unsigned ny = (unsigned) std::min(v - 1, (8 * ctx.sm_count + npo - 1) / npo);
     tau_pack_kernel<<<dim3((unsigned) npo, ny), v >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(Ts, Td, o, v, pairs_o, dst, ld,
-                                                                                             bar ? 0.5 : 1.0);
+                                                                                             bar ? 0.5 : 1.0, cm);
     ctx.launched("tau_pack");
 }
 
-// F[m][i] += sum_n G[(i,n)][(m,n)]   (G is [o*o][ldg]: the n = n' trace of an all-pairs product, cc.cpp:209)
-__global__ void pair_trace_add_kernel(const double *__restrict__ G, long long ldg, int o, double *__restrict__ F) {
+// F[m][i] += sum_n G[(i,n)][(m,n)] over the (i,n), (m,n) pairs of class all.want (G: that class's block of the all-pairs
+// product, cc.cpp:209; all.cls / all.loc over i*o + n).  Null maps: one class, G is [o*o][ldg].
+__global__ void pair_trace_add_kernel(const double *__restrict__ G, long long ldg, int o, PairColMap all, double *__restrict__ F) {
     const int n2 = o * o;
     GRID_STRIDE(lin, (long long) n2) {
         const int m = (int) (lin / o), i = (int) (lin % o);
         double s = 0.0;
-        for (int n = 0; n < o; ++n) s += G[(long long) (i * o + n) * ldg + (m * o + n)];
+        for (int n = 0; n < o; ++n) {
+            long long r, c;
+            if (pair_col(all, (size_t) i * o + n, r) && pair_col(all, (size_t) m * o + n, c)) s += G[r * ldg + c];
+        }
         F[lin] += s;
     }
 }
-void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, double *F) {
+void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, PairColMap all, double *F) {
     if (o <= 0) return;
-    pair_trace_add_kernel<<<grid_for((long long) o * o, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(G, ldg, o, F);
+    pair_trace_add_kernel<<<grid_for((long long) o * o, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(G, ldg, o, all, F);
     ctx.launched("pair_trace_add");
 }
 
 // The last step of the fused T2 equation (cc.cpp:312-383 assembled in one pass):
 //   r = <ij||ab> + P(ab) Uab + P(ij) Uij + P(ij)P(ab) Rt[i,a,b,j] + s(ij) s(ab) LP[i<j][a<b];   T2_new = r / D_ijab
 __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double *__restrict__ Uab, const double *__restrict__ Uij,
-                                   const double *__restrict__ Rt, const double *__restrict__ LP, long long ldl,
+                                   const double *__restrict__ Rt, LadderBlocks lb,
                                    const double *__restrict__ foo, const double *__restrict__ fvv, const double *__restrict__ D,
                                    int o, int v, double *__restrict__ out) {
     const long long n = (long long) o * o * v * v, vv = (long long) v * v;
@@ -826,18 +881,24 @@ __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double
             }
             const long long pij = (long long) i0 * o - (long long) i0 * (i0 + 1) / 2 + (j0 - i0 - 1);
             const long long pab = (long long) a0 * v - (long long) a0 * (a0 + 1) / 2 + (b0 - a0 - 1);
-            x += sign * LP[pij * ldl + pab];
+            // the packed ladder family: class blocks [rows of the class][columns of the class]; other classes hold exact zeros
+            if (!lb.rowcls) {
+                x += sign * lb.lp[0][pij * lb.ld[0] + pab];
+            } else {
+                const int c = lb.rowcls[pij];
+                if (lb.colcls[pab] == c) x += sign * lb.lp[c][(long long) lb.rowloc[pij] * lb.ld[c] + lb.colloc[pab]];
+            }
         }
         const double d = D ? D[lin]
                            : foo[(long long) i * o + i] + foo[(long long) j * o + j] - fvv[(long long) a * v + a] - fvv[(long long) b * v + b];
         out[lin] = x / d;
     }
 }
-void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *LP, long long ldl,
+void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const LadderBlocks &lb,
                  const double *foo, const double *fvv, const double *D, int o, int v, double *out) {
     const long long n = (long long) o * o * v * v;
     if (n == 0) return;
-    finalize_t2_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(oovv, Uab, Uij, Rt, LP, ldl, foo, fvv, D, o, v, out);
+    finalize_t2_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(oovv, Uab, Uij, Rt, lb, foo, fvv, D, o, v, out);
     ctx.launched("finalize_t2");
 }
 
@@ -857,52 +918,55 @@ void wmnij_pack(Ctx &ctx, const double *W, int o, const int *pairs_o, int npo, d
     ctx.launched("wmnij_pack");
 }
 
-// W[m,n,i,j] += s(mn) s(ij) alpha WP[p(i<j)][q(m<n)]: the packed 1/4 tau_ijef <mn||ef> term of W_mnij (cc.cpp:231)
-__global__ void wmnij_unpack_add_kernel(const double *__restrict__ WP, long long ld, int o, double alpha, double *__restrict__ W) {
-    const long long n = (long long) o * o * o * o;
+// W[m,n,i,j] += s(mn) s(ij) alpha WP[p][q] for the pairs (i<j) = list[p], (m<n) = list[q] of ONE class (the packed
+// 1/4 tau_ijef <mn||ef> term of W_mnij, cc.cpp:231); every element of W is touched by at most one (p, q, sign) combination
+__global__ void wmnij_unpack_add_kernel(const double *__restrict__ WP, long long ld, int o, const int *__restrict__ list, int np,
+                                        double alpha, double *__restrict__ W) {
+    const long long n = (long long) np * np;
     GRID_STRIDE(lin, n) {
-        long long r = lin;
-        int j = (int) (r % o);
-        r /= o;
-        int i = (int) (r % o);
-        r /= o;
-        int nn = (int) (r % o);
-        int m = (int) (r / o);
-        if (i == j || m == nn) continue;
-        double sign = alpha;
-        if (i > j) {
-            const int t = i;
-            i = j, j = t, sign = -sign;
-        }
-        if (m > nn) {
-            const int t = m;
-            m = nn, nn = t, sign = -sign;
-        }
-        const long long pij = (long long) i * o - (long long) i * (i + 1) / 2 + (j - i - 1);
-        const long long pmn = (long long) m * o - (long long) m * (m + 1) / 2 + (nn - m - 1);
-        W[lin] += sign * WP[pij * ld + pmn];
+        const int p = (int) (lin / np), q = (int) (lin % np);
+        const long long i = list[2 * p], j = list[2 * p + 1], m = list[2 * q], nn = list[2 * q + 1];
+        const double x = alpha * WP[(long long) p * ld + q];
+        W[((m * o + nn) * o + i) * o + j] += x;
+        W[((nn * o + m) * o + i) * o + j] -= x;
+        W[((m * o + nn) * o + j) * o + i] -= x;
+        W[((nn * o + m) * o + j) * o + i] += x;
     }
 }
-void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, double alpha, double *W) {
-    if (o < 2) return;
-    wmnij_unpack_add_kernel<<<grid_for((long long) o * o * o * o, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(WP, ld, o, alpha, W);
+void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, const int *list, int np, double alpha, double *W) {
+    if (np <= 0) return;
+    wmnij_unpack_add_kernel<<<grid_for((long long) np * np, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(WP, ld, o, list, np, alpha, W);
     ctx.launched("wmnij_unpack_add");
 }
 
-// LP[p][q(a<b)] -= X[p][a][b] - X[p][b][a]   (X is [npo][v][v]: the P(ab) of the tau.<am||ef>.t term on packed pairs)
-__global__ void packed_antisym_sub_kernel(const double *__restrict__ X, int v, double *__restrict__ LP, long long ld) {
-    const double *x = X + (size_t) blockIdx.x * v * v;
+// LP[p][col(a<b)] -= sum_m ( Z[p][(a,m)] t[m,b] - Z[p][(b,m)] t[m,a] ) for the rows p of one class: the
+// -1/2 P(ab) (tau.<am||ef>).t_old term (cc.cpp:237-238 inside :348) applied directly on the packed pairs.  Z's columns are
+// the (a,m) pairs of the same class (am.cls / am.loc over a*o + m); pairs of other classes are exact zeros and are skipped.
+__global__ void z_t_sub_kernel(const double *__restrict__ Z, long long ldz, const double *__restrict__ ts, int o, int v,
+                               double *__restrict__ LP, long long ld, PairColMap cm, PairColMap am) {
+    const double *z = Z + (size_t) blockIdx.x * (size_t) ldz;
     double *d = LP + (size_t) blockIdx.x * (size_t) ld;
     for (int a = blockIdx.y; a + 1 < v; a += gridDim.y) {
         const size_t q0 = (size_t) a * v - (size_t) a * (a + 1) / 2 - (a + 1);
-        for (int b = a + 1 + threadIdx.x; b < v; b += blockDim.x) d[q0 + b] -= x[(size_t) a * v + b] - x[(size_t) b * v + a];
+        for (int b = a + 1 + threadIdx.x; b < v; b += blockDim.x) {
+            long long col;
+            if (!pair_col(cm, q0 + b, col)) continue;
+            double acc = 0.0;
+            for (int m = 0; m < o; ++m) {
+                long long ca, cb;
+                if (pair_col(am, (size_t) a * o + m, ca)) acc += z[ca] * ts[(size_t) m * v + b];
+                if (pair_col(am, (size_t) b * o + m, cb)) acc -= z[cb] * ts[(size_t) m * v + a];
+            }
+            d[col] -= acc;
+        }
     }
 }
-void packed_antisym_sub(Ctx &ctx, const double *X, int npo, int v, double *LP, long long ld) {
-    if (npo <= 0 || v < 2) return;
-    const unsigned ny = (unsigned) std::min(v - 1, (8 * ctx.sm_count + npo - 1) / npo);
-    packed_antisym_sub_kernel<<<dim3((unsigned) npo, ny), v >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(X, v, LP, ld);
-    ctx.launched("packed_antisym_sub");
+void z_t_sub(Ctx &ctx, const double *Z, long long ldz, const double *Ts, int o, int v, int nrows, double *LP, long long ld, PairColMap cm,
+             PairColMap am) {
+    if (nrows <= 0 || v < 2) return;
+    const unsigned ny = (unsigned) std::min(v - 1, (8 * ctx.sm_count + nrows - 1) / nrows);
+    z_t_sub_kernel<<<dim3((unsigned) nrows, ny), v >= 2 * kBlock ? kBlock : 64, 0, ctx.stream>>>(Z, ldz, Ts, o, v, LP, ld, cm, am);
+    ctx.launched("z_t_sub");
 }
 
 __global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, long long npv, int o, int v, double *__restrict__ r) {

@@ -5,6 +5,19 @@
 
 namespace qcp2 {
 
+// Class maps of pair-packed matrices (ccsd_sym.cu): pair q belongs to class cls[q] and sits at position loc[q] of that
+// class's block; `want` selects the class a kernel works on.  Null cls: one class, natural order.
+struct PairColMap {
+    const int *cls = nullptr, *loc = nullptr;
+    int want = 0;
+};
+// the packed [i<j][a<b] accumulator of the T2 equation as one block per class (finalize_t2)
+struct LadderBlocks {
+    const double *lp[3] = {nullptr, nullptr, nullptr};
+    long long ld[3] = {0, 0, 0};
+    const int *rowcls = nullptr, *rowloc = nullptr, *colcls = nullptr, *colloc = nullptr;// null: one class, natural order
+};
+
 // out[o0..o_{r-1}] = beta*out + alpha*in[sum_d o_d * istride[d]]   (out dense row-major)
 void permute_axpby(Ctx &ctx, double *out, const double *in, int rank, const long long *out_ext,
                    const long long *in_stride_per_out_dim, double alpha, double beta);
@@ -20,7 +33,9 @@ void slice_block(Ctx &ctx, const double *so, int n2, int o, int v, const char *s
 void so_block(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec, double *out);
 // pair-packed rows: dst[row][q(e<f)] = <pairs[2 row] + m0, pairs[2 row + 1] + m1 || e + m2, f + m2>, e < f < d23
 void so_block_packed(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int m0, int m1, int m2, int d23,
-                     const int *pairs01, int n01, double *dst, long long ld);
+                     const int *pairs01, int n01, double *dst, long long ld, PairColMap cm = PairColMap());
+// res[0..3] as antisymmetry_defect_async for (a,b) and (e,f); res[4] = max |x| over the spin-forbidden elements
+void spin_pattern_defect_async(Ctx &ctx, const double *x, const long long d[4], const int off[4], unsigned long long *res);
 void so_vvvv_defect_async(Ctx &ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, unsigned long long *res);
 void make_denom(Ctx &ctx, const double *F_spin, int n2, int o, int v, double *denom);
 void make_so_moes(Ctx &ctx, const double *ea, const double *eb, int n, double *F);
@@ -51,19 +66,21 @@ void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out);
 
 // dst[row][q(e<f)] = src[a_row][b_row][e][f] for the rows (a<b) listed in pairs01 (2 ints per row); src is [d01,d01,d23,d23]
 // dst rows are `ld` doubles apart (ld >= d23 (d23-1)/2; an even ld keeps the rows 16-byte aligned for the GEMM's vector copies)
-void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld);
+void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld,
+                PairColMap cm = PairColMap());
 // r[i,j,a,b] += sgn(ij) sgn(ab) LP[p(i,j)][p(a,b)]  (zero on the diagonals); LP is [o(o-1)/2][v(v-1)/2]
 void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, double *r);
 
 // packed-pair pieces of the fused CCSD iteration (i<j rows, a<b columns; `ld` = row stride, even)
 void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,
-              bool bar = false);// rows = any list of (i,j) pairs; bar: tau-bar (Stanton eq. 10)
-void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, double *F);
-void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *LP, long long ldl,
+              bool bar = false, PairColMap cm = PairColMap());// rows = any list of (i,j) pairs; bar: tau-bar (Stanton eq. 10)
+void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, PairColMap all, double *F);
+void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const LadderBlocks &lb,
                  const double *foo, const double *fvv, const double *D, int o, int v, double *out);
 void wmnij_pack(Ctx &ctx, const double *W, int o, const int *pairs_o, int npo, double *dst, long long ld);
-void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, double alpha, double *W);
-void packed_antisym_sub(Ctx &ctx, const double *X, int npo, int v, double *LP, long long ld);
+void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, const int *list, int np, double alpha, double *W);
+void z_t_sub(Ctx &ctx, const double *Z, long long ldz, const double *Ts, int o, int v, int nrows, double *LP, long long ld, PairColMap cm,
+             PairColMap am);
 
 // max |x + P x| over an index-pair transposition, relative to max|x| -> host values
 void antisymmetry_defect(Ctx &ctx, const double *x, long long d0, long long d1, long long d2, long long d3, int pair,

@@ -426,6 +426,10 @@ class Context:
         self.check(self.lib.qcp2_so_block(self.h, _p(aa), _p(bb), _p(ab), aa.shape[0], no, nv, int_string.encode(), _p(out)))
         return out
 
+    def ccsd_last_mode(self):
+        """0 dense term list, 1 pair-packed, 2 pair-packed + spin classes (see qcp2_ccsd_last_mode)."""
+        return int(self.lib.qcp2_ccsd_last_mode(self.h))
+
     def pool_high_water(self):
         """Peak bytes of the context's workspace pool since the start of the last post_hf call."""
         return int(self.lib.qcp2_pool_high_water(self.h))

@@ -75,6 +75,9 @@ def test_configs_vs_the_reference_itself(ctx):
         assert r["iters"] == g[name]["cc_iters"], name
         assert abs(r["e_ccsd"] - g[name]["e_ccsd"]) < E_TOL, name
         assert abs(r["e_t"] - g[name]["e_t"]) < E_TOL, name
+        # RHF inputs carry the spin zero pattern of transform_to_so: pair-packed iteration, one block per spin class (mode 2);
+        # the as-written UHF integrals fail the antisymmetry checks and take the dense term list (mode 0)
+        assert ctx.ccsd_last_mode() == (0 if uhf else 2), (name, ctx.ccsd_last_mode())
 
 
 def test_config3_ch4_ccpvtz_fused_pipeline_vs_committed_cpu_oracle(ctx):
@@ -88,6 +91,14 @@ def test_config3_ch4_ccpvtz_fused_pipeline_vs_committed_cpu_oracle(ctx):
     r = ctx.post_hf(case["ao"], case["C"], None, case["eps"], None, case["no"], case["nv"], stages=3, maxiter=200, cc_conv=1e-12)
     assert abs(r["e_mp2"] - g["e_mp2"]) < E_TOL and abs(r["e_ccsd"] - g["e_ccsd"]) < E_TOL and abs(r["e_t"] - g["e_t"]) < E_TOL
     assert r["iters"] == g["iters"] and np.max(np.abs(r["e_hist"] - np.array(g["e_hist"]))) < E_TOL
+    assert ctx.ccsd_last_mode() == 2
+    # the same solve with the spin classes switched off (one class, dense pairs): identical trajectory to rounding
+    os.environ["QCP2_CCSD_NO_SPIN_BLOCKS"] = "1"
+    try:
+        d = ctx.post_hf(case["ao"], case["C"], None, case["eps"], None, case["no"], case["nv"], stages=2, maxiter=200, cc_conv=1e-12)
+    finally:
+        del os.environ["QCP2_CCSD_NO_SPIN_BLOCKS"]
+    assert ctx.ccsd_last_mode() == 1 and d["iters"] == r["iters"] and abs(d["e_ccsd"] - r["e_ccsd"]) < 1e-12
 
 
 def test_p2_driver_runs_reference_input_json(tmp_path):

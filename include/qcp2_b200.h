@@ -223,8 +223,8 @@ int qcp2_contract(qcp2_ctx *ctx, double alpha, const double *A, const long long 
 int qcp2_dgemm(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A,
                long long lda, const double *B, long long ldb, double beta, double *C, long long ldc);
 /* The same product with device pointers only, a strided batch, a forced kernel choice and device timing (tests and
- * tuning tools): tile < 0 lets the library choose; 0..5 force the warp-specialised TMA kernel's CTA tile
- * (80x256, 48x256, 16x256, 64x64, 112x128, 16x192), +8 runs the transposed problem C^T = B^T A^T on that tile; k_splits > 0
+ * tuning tools): tile < 0 lets the library choose; 0..6 force the warp-specialised TMA kernel's CTA tile
+ * (80x256, 48x256, 16x256, 64x64, 112x128, 16x192, 32x256), +8 runs the transposed problem C^T = B^T A^T on that tile; k_splits > 0
  * forces the split-K factor; the product is launched `reps` times and *seconds (may be NULL) receives the mean device
  * time of one launch.  Operands that are not 16-byte aligned take the cp.async kernel regardless of `tile`. */
 int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A, long long lda,
@@ -240,6 +240,11 @@ long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap
  * the spatial MO tensors (integrals.cpp:136-167 + 184-207 fused; bit-identical values).  out has the block's extents. */
 int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec,
                   double *out);
+/* Opt-in DIIS for the CCSD loops of this context (qcp2_ccsd, qcp2_post_hf*): nvec = 0 (default) is the reference's plain
+ * Jacobi iteration (cc.cpp:426-447: same trajectory, same iteration count); 2..12 extrapolates over the last nvec Jacobi
+ * steps (Pulay; error vector = amplitude change).  Same fixed point, fewer iterations.  The environment variable
+ * QCP2_CCSD_DIIS=nvec does the same for hosts that cannot call this (the P2 driver). */
+int qcp2_set_ccsd_diis(qcp2_ctx *ctx, int nvec);
 /* Formulation the last CCSD solve of this context ran (qcp2_ccsd, qcp2_post_hf*): 0 = the dense term list of cc.cpp (inputs
  * without the permutational symmetries of RHF-type integrals, e.g. the as-written UHF path), 1 = pair-packed / factorised
  * (ccsd_sym.cu), 2 = pair-packed with one block per spin class (the inputs carry the zero pattern of transform_to_so,

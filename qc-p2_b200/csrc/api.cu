@@ -1064,6 +1064,12 @@ int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const doubl
     });
 }
 
+int qcp2_set_ccsd_diis(qcp2_ctx *ctx, int nvec) {
+    if (!ctx || nvec < 0 || nvec == 1 || nvec > 12) return 2;
+    ctx->c.ccsd_diis = nvec;
+    return 0;
+}
+
 int qcp2_ccsd_last_mode(const qcp2_ctx *ctx) { return ctx ? ctx->c.last_ccsd_mode : -1; }
 
 long long qcp2_pool_high_water(const qcp2_ctx *ctx) {

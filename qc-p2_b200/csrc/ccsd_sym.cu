@@ -118,12 +118,28 @@ bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, const double 
     for (int i = 0; i < o; ++i)
         for (int n = 0; n < o; ++n) add(cls_of(i, n), 3, i, n, allcls, allloc);
     sp.npo = (int) rowcls.size(), sp.npv = (int) colcls.size();
+    std::vector<int> ovpos((size_t) (O * V), 0);
+    if (blocked) {
+        auto ovcls = [&](int i, int a) { return (i & 1) == ((o + a) & 1) ? 0 : 1 + (i & 1); };
+        long long next = 0;
+        for (int c = 0; c < 3; ++c) {
+            sp.ov0[c] = next;
+            for (int i = 0; i < o; ++i)
+                for (int a = 0; a < v; ++a)
+                    if (ovcls(i, a) == c) ovpos[(size_t) (i * V + a)] = (int) next++;
+            sp.ovn[c] = next - sp.ov0[c];
+            next = even(next);
+        }
+        sp.ldov = even(next);
+    }
     std::vector<int> flat;
     size_t list_off[3][4], map_off[8];
     for (int c = 0; c < sp.ncls; ++c)
         for (int w = 0; w < 4; ++w) list_off[c][w] = flat.size(), flat.insert(flat.end(), lists[c][w].begin(), lists[c][w].end());
     const std::vector<int> *maps[8] = {&rowcls, &rowloc, &colcls, &colloc, &amcls, &amloc, &allcls, &allloc};
     for (int k = 0; k < 8; ++k) map_off[k] = flat.size(), flat.insert(flat.end(), maps[k]->begin(), maps[k]->end());
+    const size_t ov_off = flat.size();
+    flat.insert(flat.end(), ovpos.begin(), ovpos.end());
     sp.ints_buf = DBuf(ctx, (flat.size() * sizeof(int) + 7) / 8 + 1);
     int *pd = reinterpret_cast<int *>(sp.ints_buf.p);
     QCP2_CUDA(cudaMemcpyAsync(pd, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx.stream));
@@ -131,6 +147,12 @@ bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, const double 
     if (blocked) {
         sp.rowcls = pd + map_off[0], sp.rowloc = pd + map_off[1], sp.colcls = pd + map_off[2], sp.colloc = pd + map_off[3];
         sp.amcls = pd + map_off[4], sp.amloc = pd + map_off[5], sp.allcls = pd + map_off[6], sp.allloc = pd + map_off[7];
+        sp.ovpos = pd + ov_off;
+        // <mn||ef> as the right operand of the blocked -1/2 t_jnfb <mn||ef> product: rows (n,f), columns (m,e), both class-sorted
+        sp.oovvS = DBuf(ctx, (size_t) (sp.ldov * sp.ldov));
+        QCP2_CUDA(cudaMemsetAsync(sp.oovvS.p, 0, (size_t) (sp.ldov * sp.ldov) * 8, ctx.stream));
+        const long long d[4] = {O, O, V, V};
+        ov_sort4(ctx, I.p[I_OOVV], d, /*row (n,f)*/ 1, 3, /*col (m,e)*/ 0, 2, v, sp.ovpos, sp.ldov, 1.0, sp.oovvS.p);
     }
     // ---- per class: the row-concatenated right operand of the tau product, <ab||ef> | <am||ef> | <mn||ef> (each segment
     // starting on an even row, so the matching column segments of the result stay 16-byte aligned), all on e<f of the class
@@ -181,7 +203,21 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     make_tau(ctx, T1, T2, o, v, true, taub);                                  // tau-bar, dense (F_ae)
     for (int c = 0; c < sp.ncls; ++c)                                         // tau(T1 old, T2) on i<j, a<b, one block per class
         if (sp.cls[c].nrow && sp.cls[c].ncol) tau_pack(ctx, T1, T2, o, v, sp.cls[c].rows, sp.cls[c].nrow, sp.cls[c].tauoP, sp.cls[c].ldk, false, colmap(c));
-    wmbej_amplitudes(ctx, nullptr, T2, o, v, tt);                             // -1/2 t_jnfb as [j,b,n,f]
+    const bool ring_blocks = sp.spin_blocked && sp.ovpos && !getenv("QCP2_CCSD_DENSE_RING");
+    const long long ldr = sp.ldov;
+    const long long t2d[4] = {O, O, V, V};
+    DBuf lfS, ttS, wS, rtS;
+    if (ring_blocks) {
+        // spin-blocked ring products: the (ov) x (ov) matrices are held over class-sorted composites (SymPack::ovpos), where
+        // t_imae, -1/2 t_jnfb, <mn||ef> and W_mbej are block matrices with ONE non-zero block per block row
+        lfS = DBuf(ctx, (size_t) (ldr * ldr)), ttS = DBuf(ctx, (size_t) (ldr * ldr)), wS = DBuf(ctx, (size_t) (ldr * ldr)),
+        rtS = DBuf(ctx, (size_t) (ldr * ldr));
+        fill_zero(ctx, lfS.p, ldr * ldr), fill_zero(ctx, ttS.p, ldr * ldr), fill_zero(ctx, rtS.p, ldr * ldr);
+        ov_sort4(ctx, T2, t2d, /*row (i,a)*/ 0, 2, /*col (m,e)*/ 1, 3, v, sp.ovpos, ldr, 1.0, lfS.p);   // t[i,m,a,e]
+        ov_sort4(ctx, T2, t2d, /*row (j,b)*/ 0, 3, /*col (n,f)*/ 1, 2, v, sp.ovpos, ldr, -0.5, ttS.p);  // -1/2 t[j,n,f,b]
+    } else {
+        wmbej_amplitudes(ctx, nullptr, T2, o, v, tt);                         // -1/2 t_jnfb as [j,b,n,f]
+    }
     {
         const long long ext[4] = {O, V, O, V}, istr[4] = {O * V * V, V, V * V, 1};// t[i,m,a,e] read as [i,a,m,e]
         permute_axpby(ctx, lf.p, T2, 4, ext, istr, 1.0, 0.0);
@@ -238,7 +274,25 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
         const TView P2(p2.p, {O, O, V, O});
         contract(ctx, 1.0, ts, "jf", oovv, "mnef", 1.0, P2, "mnej", I.p[I_OOVO]);              // <mn||ej> + sum_f t_jf <mn||ef>
         contract(ctx, -1.0, ts, "nb", P2, "mnej", 1.0, Wm, "mebj");                            // :246 + the t.t part of :249
-        contract(ctx, 1.0, TView(tt.p, {O, V, O, V}), "jbnf", oovv, "mnef", 1.0, Wm, "mebj");  // :247
+        if (!ring_blocks) {
+            contract(ctx, 1.0, TView(tt.p, {O, V, O, V}), "jbnf", oovv, "mnef", 1.0, Wm, "mebj");// :247
+        } else {
+            // :247 per spin block: C[(j,b) r][(m,e) c] = ttS[r][k] . <mn||ef>S[k][c], added into W[(m,e)][(j,b)] (transposed store)
+            fill_zero(ctx, wS.p, ldr * ldr);
+            const long long wd[4] = {O, V, V, O};
+            ov_sort4(ctx, wm.p, wd, /*row (m,e)*/ 0, 1, /*col (j,b)*/ 3, 2, v, sp.ovpos, ldr, 1.0, wS.p);
+            static const int rkc[3][3] = {{0, 0, 0}, {1, 2, 1}, {2, 1, 2}};
+            for (int q = 0; q < 3; ++q) {
+                const int r = rkc[q][0], kk = rkc[q][1], c = rkc[q][2];
+                if (!sp.ovn[r] || !sp.ovn[kk] || !sp.ovn[c]) continue;
+                GemmArgs g;// computed as the transposed problem so that the store is row-major: W[c rows][r cols] += S[k][c]^T . tt[r][k]^T
+                g.M = (int) sp.ovn[c], g.N = (int) sp.ovn[r], g.K = (int) sp.ovn[kk], g.beta = 1.0;
+                g.A = sp.oovvS.p + sp.ov0[kk] * ldr + sp.ov0[c], g.lda = ldr;// [K][M]
+                g.B = ttS.p + sp.ov0[r] * ldr + sp.ov0[kk], g.ldb = ldr;      // [N][K]
+                g.C = wS.p + sp.ov0[c] * ldr + sp.ov0[r], g.ldc = ldr;
+                gemm(ctx, g, false, false);
+            }
+        }
     }
 
     // ---------------------------------------------------------------- T1 equation, cc.cpp:257-292 (Stanton eq. 1)
@@ -313,8 +367,23 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     const TView Rt(rt.p, {O, V, V, O}), P1(p1.p, {O, O, V, O});
     contract(ctx, 1.0, tn, "ie", ovov, "mbje", 0.0, P1, "imbj");
     contract(ctx, 1.0, tn, "ma", P1, "imbj", 0.0, Rt, "iabj");                                 // :360-363 (first writer)
-    contract(ctx, 1.0, Lf, "iame", Wm, "mebj", 1.0, Rt, "iabj");                               // :354-357
-    finalize_t2(ctx, I.p[I_OOVV], uab, uij, rt, lb, foo, fvv, nullptr, o, v, T2n);             // :312, P(..) combines, :374-383
+    if (!ring_blocks) {
+        contract(ctx, 1.0, Lf, "iame", Wm, "mebj", 1.0, Rt, "iabj");                           // :354-357
+    } else {
+        static const int rkc[3][3] = {{0, 0, 0}, {1, 2, 2}, {2, 1, 1}};// (class of (i,a), of (m,e), of (j,b))
+        for (int q = 0; q < 3; ++q) {
+            const int r = rkc[q][0], kk = rkc[q][1], c = rkc[q][2];
+            if (!sp.ovn[r] || !sp.ovn[kk] || !sp.ovn[c]) continue;
+            GemmArgs g;
+            g.M = (int) sp.ovn[r], g.N = (int) sp.ovn[c], g.K = (int) sp.ovn[kk];
+            g.A = lfS.p + sp.ov0[r] * ldr + sp.ov0[kk], g.lda = ldr;// [M][K]
+            g.B = wS.p + sp.ov0[kk] * ldr + sp.ov0[c], g.ldb = ldr;  // [K][N]
+            g.C = rtS.p + sp.ov0[r] * ldr + sp.ov0[c], g.ldc = ldr;
+            gemm(ctx, g, true, true);
+        }
+    }
+    finalize_t2(ctx, I.p[I_OOVV], uab, uij, rt, ring_blocks ? rtS.p : nullptr, sp.ovpos, ldr, lb, foo, fvv, nullptr, o, v,
+                T2n);                                                                          // :312, P(..) combines, :374-383
 }
 
 }// namespace qcp2

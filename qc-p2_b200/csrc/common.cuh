@@ -58,6 +58,7 @@ struct Ctx {
     long long launches = 0;
     std::string last_error;
     double ccsd_loop_seconds = 0.0;
+    int ccsd_diis = 0;      // opt-in DIIS subspace size of the CCSD loop (qcp2_set_ccsd_diis; 0 = the reference's plain Jacobi loop)
     int last_ccsd_mode = -1;// formulation the last CCSD solve used: 0 dense term list, 1 pair-packed, 2 pair-packed + spin classes
     PermCache *perm_cache = nullptr;
     // row-sharded GEMMs (dgemm.cu): while set, every product above shard_min_flops whose result is a dense row-major

@@ -53,6 +53,7 @@ void ws_dispatch(Ctx &ctx, int shape, const CUtensorMap &ta, const CUtensorMap &
         case WS_16x256: ws_launch_16x256(ctx, ta, tb, w, a_kc, b_nc); break;
         case WS_64x64: ws_launch_64x64(ctx, ta, tb, w, a_kc, b_nc); break;
         case WS_16x192: ws_launch_16x192(ctx, ta, tb, w, a_kc, b_nc); break;
+        case WS_32x256: ws_launch_32x256(ctx, ta, tb, w, a_kc, b_nc); break;
         default: ws_launch_112x128(ctx, ta, tb, w, a_kc, b_nc); break;
     }
 }
@@ -108,7 +109,7 @@ struct WsChoice {
 // fragment-load efficiency, or bound by streaming its operand bytes at the chip's ~3400 B/clk HBM rate shared by the
 // CTAs of a wave), plus the split-K partial traffic
 WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
-    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.65, 0.92, 0.68};
+    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.65, 0.92, 0.68, 0.80};
     WsChoice best{WS_64x64, false, 1, 1e300};
     const int nkb = (g.K + WS_BK - 1) / WS_BK;
     for (int swap = 0; swap < 2; ++swap) {
@@ -117,7 +118,8 @@ WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
             const WsShapeInfo &sh = kWsShapes[t];
             if ((t == WS_16x256 || t == WS_16x192) && M > 16) continue;
             if (t == WS_48x256 && M > 48) continue;
-            if (swap && t != WS_16x256 && t != WS_16x192 && t != WS_48x256) continue;// the transposed problem only to reach the skinny-M tiles
+            if (t == WS_32x256 && M > 32) continue;
+            if (swap && t != WS_16x256 && t != WS_16x192 && t != WS_48x256 && t != WS_32x256) continue;// the transposed problem only to reach the skinny-M tiles
             const long long tiles = ((M + sh.bm - 1) / sh.bm) * ((N + sh.bn - 1) / sh.bn) * g.batch;
             const long long slots = ctx.sm_count;
             int cands[16], nc = 0;

@@ -380,6 +380,82 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
         QCP2_CUDA(cudaMemcpyAsync(T1, t1n.p, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
         QCP2_CUDA(cudaMemcpyAsync(T2, t2n.p, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     };
+    // ---- opt-in DIIS (qcp2_set_ccsd_diis / QCP2_CCSD_DIIS=n; NOT in the reference, whose loop cc.cpp:426-447 is the plain
+    // Jacobi iteration above -- off by default so that trajectories and iteration counts stay the reference's).
+    // After each Jacobi step x_k = (T1, T2) with error e_k = x_k - x_{k-1}, the amplitudes are replaced by sum_k c_k x_k,
+    // c minimising |sum c_k e_k| under sum c_k = 1 (Pulay), over the last `ndiis` steps.
+    // Only the symmetric formulation extrapolates: the as-written UHF equations (dense term list) have more than
+    // one fixed point -- measured on NH2/cc-pVDZ, DIIS converges to E_CCSD -0.15354 where the reference's Jacobi loop reaches
+    // -0.15740 -- so there the request is ignored and the reference's trajectory kept.
+    const int ndiis_req = ctx.ccsd_diis > 0 ? ctx.ccsd_diis : (getenv("QCP2_CCSD_DIIS") ? atoi(getenv("QCP2_CCSD_DIIS")) : 0);
+    const int ndiis = sym ? ndiis_req : 0;
+    const long long nx = O * V + o2v2;
+    DBuf dx, de, dprev, ddots, dcoef;
+    std::vector<double> Bm;// ndiis x ndiis Gram matrix of the stored errors (host)
+    int dcount = 0;
+    if (ndiis >= 2) {
+        QCP2_REQUIRE(ndiis <= 12, "CCSD DIIS: at most 12 vectors");
+        dx = DBuf(ctx, (size_t) (ndiis * nx)), de = DBuf(ctx, (size_t) (ndiis * nx)), dprev = DBuf(ctx, (size_t) nx);
+        ddots = DBuf(ctx, (size_t) ndiis), dcoef = DBuf(ctx, (size_t) ndiis);
+        Bm.assign((size_t) ndiis * ndiis, 0.0);
+    }
+    auto diis_before = [&]() {// remember x_{k-1}
+        if (ndiis < 2) return;
+        QCP2_CUDA(cudaMemcpyAsync(dprev.p, T1, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        QCP2_CUDA(cudaMemcpyAsync(dprev.p + O * V, T2, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+    };
+    auto diis_after = [&]() {
+        if (ndiis < 2) return;
+        const int slot = dcount % ndiis;
+        double *xs = dx.p + (long long) slot * nx, *es = de.p + (long long) slot * nx;
+        QCP2_CUDA(cudaMemcpyAsync(xs, T1, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        QCP2_CUDA(cudaMemcpyAsync(xs + O * V, T2, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        QCP2_CUDA(cudaMemcpyAsync(es, xs, (size_t) nx * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        axpby(ctx, es, dprev.p, -1.0, 1.0, nx);// e = x_new - x_old
+        ++dcount;
+        const int m = std::min(dcount, ndiis);
+        dots(ctx, es, de.p, nx, nx, m, ddots.p);
+        std::vector<double> row((size_t) m);
+        QCP2_CUDA(cudaMemcpyAsync(row.data(), ddots.p, (size_t) m * 8, cudaMemcpyDeviceToHost, ctx.stream));
+        ctx.sync();
+        for (int j = 0; j < m; ++j) Bm[(size_t) slot * ndiis + j] = Bm[(size_t) j * ndiis + slot] = row[(size_t) j];
+        if (m < 2) return;
+        // [B 1; 1 0] [c; lambda] = [0; 1], scaled by the largest diagonal element; Gaussian elimination with partial pivoting
+        const int n1 = m + 1;
+        std::vector<double> A((size_t) n1 * n1, 0.0), rhs((size_t) n1, 0.0);
+        double scale = 0.0;
+        for (int j = 0; j < m; ++j) scale = std::max(scale, std::fabs(Bm[(size_t) j * ndiis + j]));
+        if (!(scale > 0.0)) return;// converged to the last bit: nothing to extrapolate
+        for (int a = 0; a < m; ++a)
+            for (int b = 0; b < m; ++b) A[(size_t) a * n1 + b] = Bm[(size_t) a * ndiis + b] / scale;
+        for (int a = 0; a < m; ++a) A[(size_t) a * n1 + m] = A[(size_t) m * n1 + a] = 1.0;
+        rhs[(size_t) m] = 1.0;
+        for (int col = 0; col < n1; ++col) {
+            int piv = col;
+            for (int r = col + 1; r < n1; ++r)
+                if (std::fabs(A[(size_t) r * n1 + col]) > std::fabs(A[(size_t) piv * n1 + col])) piv = r;
+            if (std::fabs(A[(size_t) piv * n1 + col]) < 1e-14) return;// singular subspace: keep the Jacobi step
+            if (piv != col) {
+                for (int c2 = 0; c2 < n1; ++c2) std::swap(A[(size_t) piv * n1 + c2], A[(size_t) col * n1 + c2]);
+                std::swap(rhs[(size_t) piv], rhs[(size_t) col]);
+            }
+            for (int r = col + 1; r < n1; ++r) {
+                const double f = A[(size_t) r * n1 + col] / A[(size_t) col * n1 + col];
+                for (int c2 = col; c2 < n1; ++c2) A[(size_t) r * n1 + c2] -= f * A[(size_t) col * n1 + c2];
+                rhs[(size_t) r] -= f * rhs[(size_t) col];
+            }
+        }
+        std::vector<double> sol((size_t) n1, 0.0);
+        for (int r = n1 - 1; r >= 0; --r) {
+            double acc = rhs[(size_t) r];
+            for (int c2 = r + 1; c2 < n1; ++c2) acc -= A[(size_t) r * n1 + c2] * sol[(size_t) c2];
+            sol[(size_t) r] = acc / A[(size_t) r * n1 + r];
+        }
+        QCP2_CUDA(cudaMemcpyAsync(dcoef.p, sol.data(), (size_t) m * 8, cudaMemcpyHostToDevice, ctx.stream));
+        combine(ctx, dx.p, nx, m, dcoef.p, O * V, T1);
+        combine(ctx, dx.p + O * V, nx, m, dcoef.p, o2v2, T2);
+        ctx.sync();// sol is pageable
+    };
     bool use_graph = getenv("QCP2_CCSD_NO_GRAPH") == nullptr && ctx.shard == nullptr;// (NCCL calls stay outside graphs)
     cudaGraphExec_t graph_exec = nullptr;
     long long graph_launches = 0;
@@ -391,8 +467,10 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
         e_last = e;
         if (e_hist_host) e_hist_host[it] = e;
         if (std::fabs(de) < conv) break;                                                   // :438 (fabs)
+        diis_before();
         if (!use_graph || it == 0) {// the first iteration runs eagerly: it fills the re-layout cache and configures the kernels
             body();
+            diis_after();
             continue;
         }
         if (!graph_exec) {
@@ -416,6 +494,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
                 ctx.launches = l0;
                 use_graph = false;
                 body();
+                diis_after();
                 continue;
             }
             graph_launches = ctx.launches - l0;
@@ -423,6 +502,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
         }
         QCP2_CUDA(cudaGraphLaunch(graph_exec, ctx.stream));
         ctx.launches += graph_launches;
+        diis_after();
     }
     if (graph_exec) {
         cudaStreamSynchronize(ctx.stream);

@@ -34,6 +34,11 @@ struct SymPack {
         const int *rows = nullptr, *cols = nullptr, *ams = nullptr, *alls = nullptr;// device pair lists (2 ints per pair)
         DBuf ladB, oovvA, tauoP;                  // [<ab||ef>; <am||ef>; <mn||ef>][e<f], <(m,n)||ef> all ordered pairs, tau(T1 old, T2)
     } cls[3];
+    // spin-blocked only: (occupied, virtual) composites i*v + a in class-sorted order (class 0: same spin, 1: i alpha / a beta,
+    // 2: i beta / a alpha; every class starts on an even position), and <mn||ef> as the matrix [pos(n,f)][pos(m,e)]
+    const int *ovpos = nullptr;
+    long long ov0[3] = {0, 0, 0}, ovn[3] = {0, 0, 0}, ldov = 0;
+    DBuf oovvS;
     // class / position of every natural pair index (null when ncls == 1: natural order)
     const int *rowcls = nullptr, *rowloc = nullptr, *colcls = nullptr, *colloc = nullptr, *amcls = nullptr, *amloc = nullptr,
               *allcls = nullptr, *allloc = nullptr;

@@ -507,6 +507,71 @@ __device__ __forceinline__ double block_sum(double v) {
     if (w == 0) v = warp_sum(v);
     return v;// valid in thread 0
 }
+// out[pos[x_ro * V + x_rv] * ld + pos[x_co * V + x_cv]] = alpha * src[x0,x1,x2,x3]: a 4-index tensor re-laid out as a matrix
+// over (occupied, virtual) composite indices in the class-sorted order pos[] (ccsd_sym.cu, spin-blocked ring products);
+// ro / rv / co / cv select which of the four source indices form the row and column composites.
+__global__ void ov_sort4_kernel(const double *__restrict__ src, long long d0, long long d1, long long d2, long long d3, int ro, int rv,
+                                int co, int cv, int V, const int *__restrict__ pos, long long ld, double alpha, double *__restrict__ out) {
+    const long long n = d0 * d1 * d2 * d3;
+    GRID_STRIDE(lin, n) {
+        long long r = lin;
+        int x[4];
+        x[3] = (int) (r % d3);
+        r /= d3;
+        x[2] = (int) (r % d2);
+        r /= d2;
+        x[1] = (int) (r % d1);
+        x[0] = (int) (r / d1);
+        out[(long long) pos[x[ro] * V + x[rv]] * ld + pos[x[co] * V + x[cv]]] = alpha * src[lin];
+    }
+}
+void ov_sort4(Ctx &ctx, const double *src, const long long d[4], int ro, int rv, int co, int cv, int V, const int *pos, long long ld,
+              double alpha, double *out) {
+    const long long n = d[0] * d[1] * d[2] * d[3];
+    if (n == 0) return;
+    ov_sort4_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(src, d[0], d[1], d[2], d[3], ro, rv, co, cv, V, pos, ld, alpha, out);
+    ctx.launched("ov_sort4");
+}
+
+// DIIS (opt-in; not in the reference, cc.cpp:426-447 is a plain Jacobi loop): out[j] = <e_new, E[j]> for the nvec stored error
+// vectors (rows of E, `stride` doubles apart), deterministic two-stage reduction
+__global__ void dots_kernel(const double *__restrict__ e_new, const double *__restrict__ E, long long stride, long long n,
+                            double *__restrict__ partial) {
+    const double *ej = E + (long long) blockIdx.y * stride;
+    double s = 0.0;
+    GRID_STRIDE(lin, n) s += e_new[lin] * ej[lin];
+    s = block_sum(s);
+    if (threadIdx.x == 0) partial[(long long) blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+__global__ void finish_rows_kernel(const double *__restrict__ partial, int n, double *__restrict__ out) {
+    double v = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) v += partial[(long long) blockIdx.x * n + k];
+    v = block_sum(v);
+    if (threadIdx.x == 0) out[blockIdx.x] = v;
+}
+void dots(Ctx &ctx, const double *e_new, const double *E, long long stride, long long n, int nvec, double *out_dev) {
+    if (nvec <= 0) return;
+    DBuf partial(ctx, (size_t) kRedBlocks * nvec);
+    dots_kernel<<<dim3(kRedBlocks, (unsigned) nvec), kBlock, 0, ctx.stream>>>(e_new, E, stride, n, partial);
+    ctx.launched("diis_dots");
+    finish_rows_kernel<<<nvec, kBlock, 0, ctx.stream>>>(partial, kRedBlocks, out_dev);
+    ctx.launched("finish_rows");
+}
+// out = sum_k c[k] X[k]  (rows of X `stride` doubles apart; c on the device)
+__global__ void combine_kernel(const double *__restrict__ X, long long stride, int nvec, const double *__restrict__ c, long long n,
+                               double *__restrict__ out) {
+    GRID_STRIDE(lin, n) {
+        double s = 0.0;
+        for (int k = 0; k < nvec; ++k) s += c[k] * X[(long long) k * stride + lin];
+        out[lin] = s;
+    }
+}
+void combine(Ctx &ctx, const double *X, long long stride, int nvec, const double *c_dev, long long n, double *out) {
+    if (n <= 0 || nvec <= 0) return;
+    combine_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(X, stride, nvec, c_dev, n, out);
+    ctx.launched("diis_combine");
+}
+
 __global__ void finish_sum_kernel(const double *__restrict__ partial, int n, double *__restrict__ out) {
     double v = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
@@ -851,7 +916,8 @@ void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, PairColMap 
 // The last step of the fused T2 equation (cc.cpp:312-383 assembled in one pass):
 //   r = <ij||ab> + P(ab) Uab + P(ij) Uij + P(ij)P(ab) Rt[i,a,b,j] + s(ij) s(ab) LP[i<j][a<b];   T2_new = r / D_ijab
 __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double *__restrict__ Uab, const double *__restrict__ Uij,
-                                   const double *__restrict__ Rt, LadderBlocks lb,
+                                   const double *__restrict__ Rt, const double *__restrict__ RtS, const int *__restrict__ ovpos, long long ldr,
+                                   LadderBlocks lb,
                                    const double *__restrict__ foo, const double *__restrict__ fvv, const double *__restrict__ D,
                                    int o, int v, double *__restrict__ out) {
     const long long n = (long long) o * o * v * v, vv = (long long) v * v;
@@ -868,6 +934,10 @@ __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double
         auto at = [&](int x, int c, int d, int y) { return Rt[(((long long) x * v + c) * v + d) * o + y]; };
         double x = oovv[lin] + (Uab[lin] - Uab[ijba]) + (Uij[lin] - Uij[jiab]);
         x += at(i, a, b, j) - at(j, a, b, i) - at(i, b, a, j) + at(j, b, a, i);
+        if (RtS) {// the (ov)^3 part of the ring terms, held as a matrix over class-sorted (i,a) x (j,b) composites
+            const long long ia = ovpos[i * v + a], ib = ovpos[i * v + b], ja = ovpos[j * v + a], jb = ovpos[j * v + b];
+            x += RtS[ia * ldr + jb] - RtS[ja * ldr + ib] - RtS[ib * ldr + ja] + RtS[jb * ldr + ia];
+        }
         if (i != j && a != b) {
             int i0 = i, j0 = j, a0 = a, b0 = b;
             double sign = 1.0;
@@ -894,11 +964,12 @@ __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double
         out[lin] = x / d;
     }
 }
-void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const LadderBlocks &lb,
+void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *RtS,
+                 const int *ovpos, long long ldr, const LadderBlocks &lb,
                  const double *foo, const double *fvv, const double *D, int o, int v, double *out) {
     const long long n = (long long) o * o * v * v;
     if (n == 0) return;
-    finalize_t2_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(oovv, Uab, Uij, Rt, lb, foo, fvv, D, o, v, out);
+    finalize_t2_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(oovv, Uab, Uij, Rt, RtS, ovpos, ldr, lb, foo, fvv, D, o, v, out);
     ctx.launched("finalize_t2");
 }
 

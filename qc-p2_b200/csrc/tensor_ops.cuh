@@ -56,6 +56,9 @@ void divide_D_ijab(Ctx &ctx, const double *r, const double *foo, const double *f
 void divide_elementwise(Ctx &ctx, const double *r, const double *D, long long n, double *out);
 void ccsd_energy(Ctx &ctx, const double *Ts, const double *Td, const double *oovv, const double *fov, int o, int v,
                  double *e_dev);
+// DIIS building blocks: out_dev[j] = <e_new, E[j]>, j < nvec; out = sum_k c_dev[k] X[k]
+void dots(Ctx &ctx, const double *e_new, const double *E, long long stride, long long n, int nvec, double *out_dev);
+void combine(Ctx &ctx, const double *X, long long stride, int nvec, const double *c_dev, long long n, double *out);
 void extract_diag(Ctx &ctx, const double *F, int n, double *d);
 // r[i,j,a,b] += Rt[i,a,b,j] - Rt[j,a,b,i] - Rt[i,b,a,j] + Rt[j,b,a,i]   (P(ij)P(ab) of one ring product)
 void ring_combine(Ctx &ctx, const double *Rt, int o, int v, double *r);
@@ -75,7 +78,11 @@ void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, do
 void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,
               bool bar = false, PairColMap cm = PairColMap());// rows = any list of (i,j) pairs; bar: tau-bar (Stanton eq. 10)
 void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, PairColMap all, double *F);
-void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const LadderBlocks &lb,
+// Rt: [i,a,b,j]; RtS (may be null): matrix [pos(i,a)][pos(j,b)] with row stride ldr over class-sorted composites
+void ov_sort4(Ctx &ctx, const double *src, const long long d[4], int ro, int rv, int co, int cv, int V, const int *pos, long long ld,
+              double alpha, double *out);
+void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *RtS,
+                 const int *ovpos, long long ldr, const LadderBlocks &lb,
                  const double *foo, const double *fvv, const double *D, int o, int v, double *out);
 void wmnij_pack(Ctx &ctx, const double *W, int o, const int *pairs_o, int npo, double *dst, long long ld);
 void wmnij_unpack_add(Ctx &ctx, const double *WP, long long ld, int o, const int *list, int np, double alpha, double *W);

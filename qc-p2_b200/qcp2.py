@@ -426,6 +426,10 @@ class Context:
         self.check(self.lib.qcp2_so_block(self.h, _p(aa), _p(bb), _p(ab), aa.shape[0], no, nv, int_string.encode(), _p(out)))
         return out
 
+    def set_ccsd_diis(self, nvec):
+        """Opt-in DIIS over the last nvec Jacobi steps (0 = the reference's plain Jacobi loop)."""
+        self.check(self.lib.qcp2_set_ccsd_diis(self.h, int(nvec)))
+
     def ccsd_last_mode(self):
         """0 dense term list, 1 pair-packed, 2 pair-packed + spin classes (see qcp2_ccsd_last_mode)."""
         return int(self.lib.qcp2_ccsd_last_mode(self.h))

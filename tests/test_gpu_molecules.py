@@ -80,6 +80,37 @@ def test_configs_vs_the_reference_itself(ctx):
         assert ctx.ccsd_last_mode() == (0 if uhf else 2), (name, ctx.ccsd_last_mode())
 
 
+def test_opt_in_diis_reaches_the_same_ccsd_energy_in_fewer_iterations(ctx):
+    """DIIS is not in the reference (cc.cpp:426-447 is a plain Jacobi loop) and is OFF by default; switched on it must reach
+    the same fixed point (1e-10 Eh) in fewer iterations.  The as-written UHF equations have several fixed points,
+    so the dense formulation ignores the request and keeps the reference's trajectory."""
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_energies.json")))
+    for name in ("water_ccpvdz_rhf", "nh2_ccpvdz_uhf"):
+        cfg = CONFIGS[name]
+        case = molecule_case(**cfg)
+        uhf = cfg.get("uhf", False)
+        if uhf:
+            b = np.load(os.path.join(ROOT, "tests", "golden", "reference_nh2_boundary.npz"))
+            Ca, Cb, ea, eb = b["Ca"], b["Cb"], b["eps_a"], b["eps_b"]
+        else:
+            Ca, Cb, ea, eb = case["C"], None, case["eps"], None
+        ctx.set_ccsd_diis(6)
+        try:
+            r = ctx.post_hf(case["ao"], Ca, Cb, ea, eb, case["no"], case["nv"], uhf=uhf, stages=3, maxiter=200, cc_conv=1e-12)
+        finally:
+            ctx.set_ccsd_diis(0)
+        assert abs(r["e_ccsd"] - g[name]["e_ccsd"]) < E_TOL, (name, r["e_ccsd"], g[name]["e_ccsd"])
+        assert abs(r["e_t"] - g[name]["e_t"]) < 1e-9, name
+        if uhf:
+            assert r["iters"] == g[name]["cc_iters"], (name, r["iters"])
+        else:
+            assert r["iters"] < g[name]["cc_iters"], (name, r["iters"], g[name]["cc_iters"])
+    # and off again: the reference's iteration count is back
+    case = molecule_case(**CONFIGS["water_ccpvdz_rhf"])
+    r = ctx.post_hf(case["ao"], case["C"], None, case["eps"], None, case["no"], case["nv"], stages=2, maxiter=200, cc_conv=1e-12)
+    assert r["iters"] == g["water_ccpvdz_rhf"]["cc_iters"]
+
+
 def test_config3_ch4_ccpvtz_fused_pipeline_vs_committed_cpu_oracle(ctx):
     """BASELINE.json config 3 (o=10, v=162): the CPU side takes ~15 min, so its numbers are committed
     (tests/golden/ch4_ccpvtz_oracle.json, generator beside it).  The host SCF is deterministic, so

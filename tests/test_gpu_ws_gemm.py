@@ -9,7 +9,7 @@ import qcp2_b200
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-TILES = {0: (80, 256), 1: (48, 256), 2: (16, 256), 3: (64, 64), 4: (112, 128), 5: (16, 192)}
+TILES = {0: (80, 256), 1: (48, 256), 2: (16, 256), 3: (64, 64), 4: (112, 128), 5: (16, 192), 6: (32, 256)}
 
 
 @pytest.fixture(scope="module")
@@ -59,7 +59,7 @@ def _check(dctx, M, N, K, tA, tB, tile, split=0, batch=1, alpha=0.75, beta=-0.5,
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_every_tile_and_layout_with_edges(dctx, tile, tA, tB):
     bm, bn = TILES[tile]
-    m_cap = bm if tile in (1, 2, 5) else 3 * bm  # the skinny tiles are chosen for M <= 48 / 16 only
+    m_cap = bm if tile in (1, 2, 5, 6) else 3 * bm  # the skinny tiles are chosen for M <= 48 / 16 only
     for (M, N, K) in [(min(m_cap, bm + 3), bn + 5, 37), (min(m_cap, 2 * bm), 2 * bn, 64), (min(m_cap, 7), 9, 5), (min(m_cap, bm - 1), 3 * bn - 2, 16 * 9 + 1)]:
         _check(dctx, M, N, K, tA, tB, tile, seed=M + N + K)
 

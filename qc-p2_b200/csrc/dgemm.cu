@@ -109,7 +109,7 @@ struct WsChoice {
 // fragment-load efficiency, or bound by streaming its operand bytes at the chip's ~3400 B/clk HBM rate shared by the
 // CTAs of a wave), plus the split-K partial traffic
 WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
-    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.65, 0.92, 0.68, 0.80};
+    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.85, 0.92, 0.68, 0.80};
     WsChoice best{WS_64x64, false, 1, 1e300};
     const int nkb = (g.K + WS_BK - 1) / WS_BK;
     for (int swap = 0; swap < 2; ++swap) {
@@ -136,7 +136,7 @@ WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
                 // rows past the M / N edge are zero-filled by the copy engine without memory traffic
                 const double rows = (double) std::min<long long>(sh.bm, M) + (double) std::min<long long>(sh.bn, N);
                 const double bytes = rows * 16.0 * 8.0 * kb * conc / 3400.0 + 1500.0;            // clocks per wave, HBM-bound (+ fill latency)
-                double cost = waves * std::max(mma, bytes);
+                double cost = waves * (std::max(mma, bytes) + 4000.0 + 0.25 * sh.bm * sh.bn);// + per-CTA prologue / epilogue
                 // split-K: every CTA writes its partial tile; the last CTA of a tile reads all of them back (~150 B/clk)
                 if (split > 1) cost += 8.0 * sh.bm * sh.bn * (double) ctas / 6000.0 + 8.0 * sh.bm * sh.bn * split / 150.0 + 600.0;
                 if (cost < best.cost) best = WsChoice{t, swap != 0, split, cost};

@@ -248,14 +248,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         }
     }
 
-    // ---- split-K: publish the partial tile; only the last CTA of this tile continues into the epilogue
+    // ---- split-K: publish the partial tile; only the last CTA of this tile continues into the epilogue.
+    // Fragments that lie entirely past the M / N edge (most of a skinny tile) are neither published nor reduced.
     if (g.k_splits > 1) {
         const long long slot = ((long long) bz * gridDim.x + tile) * g.k_splits;
         double2 *mine = g.ws + (slot + blockIdx.y) * (FM * FN * 256) + tid;
+        bool live[FM][FN];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
 #pragma unroll
-            for (int j = 0; j < FN; ++j) mine[(i * FN + j) * 256] = make_double2(acc[i][j][0], acc[i][j][1]);
+            for (int j = 0; j < FN; ++j) {
+                live[i][j] = (m0 + (i * NWM + w_m) * 8 < g.M) && (n0 + (j * NWN + w_n) * 8 < g.N);
+                if (live[i][j]) mine[(i * FN + j) * 256] = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
         __threadfence();
         consumer_bar();
         if (tid == 0) {
@@ -266,28 +271,54 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         if (*flag != (unsigned int) g.k_splits - 1) return;
         __threadfence();
         const double2 *all = g.ws + slot * (FM * FN * 256) + tid;
+        constexpr long long SPLIT_STRIDE = (long long) FM * FN * 256;
+        // Each element is summed in split order (the result does not depend on which CTA arrived last).  The loads are
+        // issued in independent batches -- a few splits: the splits of a whole fragment row at once; many splits: sixteen
+        // splits of one fragment at once -- so the walk over the partials is bandwidth- rather than latency-bound.
+        if (g.k_splits <= 4) {
 #pragma unroll
-        for (int i = 0; i < FM; ++i)
+            for (int i = 0; i < FM; ++i) {
+                double2 p[FN][4];
 #pragma unroll
-            for (int j = 0; j < FN; ++j) {
-                double s0 = 0.0, s1 = 0.0;
-                // split order: the sum does not depend on which CTA arrived last.  Eight independent loads are in
-                // flight before the first add, so the walk over the partials is bandwidth- rather than latency-bound.
-                const double2 *src = all + (i * FN + j) * 256;
-                int q = 0;
-                for (; q + 8 <= g.k_splits; q += 8) {
-                    double2 p[8];
+                for (int j = 0; j < FN; ++j)
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) p[u] = __ldcg(src + (long long) (q + u) * (FM * FN * 256));
+                    for (int q = 0; q < 4; ++q)
+                        p[j][q] = (live[i][j] && q < g.k_splits) ? __ldcg(all + q * SPLIT_STRIDE + (i * FN + j) * 256) : make_double2(0.0, 0.0);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) s0 += p[u].x, s1 += p[u].y;
+                for (int j = 0; j < FN; ++j) {
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q < g.k_splits) s0 += p[j][q].x, s1 += p[j][q].y;
+                    acc[i][j][0] = s0, acc[i][j][1] = s1;
                 }
-                for (; q < g.k_splits; ++q) {
-                    const double2 p = __ldcg(src + (long long) q * (FM * FN * 256));
-                    s0 += p.x, s1 += p.y;
-                }
-                acc[i][j][0] = s0, acc[i][j][1] = s1;
             }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FM; ++i)
+#pragma unroll
+                for (int j = 0; j < FN; ++j) {
+                    double s0 = 0.0, s1 = 0.0;
+                    if (live[i][j]) {
+                        const double2 *src = all + (i * FN + j) * 256;
+                        int q = 0;
+                        for (; q + 16 <= g.k_splits; q += 16) {
+                            double2 p[16];
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) p[u] = __ldcg(src + (long long) (q + u) * SPLIT_STRIDE);
+#pragma unroll
+                            for (int u = 0; u < 16; ++u) s0 += p[u].x, s1 += p[u].y;
+                        }
+                        double2 p[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) p[u] = (q + u < g.k_splits) ? __ldcg(src + (long long) (q + u) * SPLIT_STRIDE) : make_double2(0.0, 0.0);
+#pragma unroll
+                        for (int u = 0; u < 16; ++u)
+                            if (q + u < g.k_splits) s0 += p[u].x, s1 += p[u].y;
+                    }
+                    acc[i][j][0] = s0, acc[i][j][1] = s1;
+                }
+        }
         if (tid == 0) g.counters[(long long) bz * gridDim.x + tile] = 0u;// ready for the next launch
     }
 

@@ -64,7 +64,7 @@ struct Ctx {
     // row-sharded GEMMs (dgemm.cu): while set, every product above shard_min_flops whose result is a dense row-major
     // matrix is split by rows over the communicator's ranks and re-assembled with one broadcast per rank
     struct Comm *shard = nullptr;
-    double shard_min_flops = 2.0e9;
+    double shard_min_flops = 8.0e9;// r2: the spin-blocked / packed products of real molecules are below it (sharding them cost 12 % at CH4/cc-pVTZ)
     long long sharded_gemms = 0;
     // split-K tile counters of the warp-specialised GEMM (dgemm_ws.cuh): zero between launches (the last CTA of a
     // tile resets its counter), allocated with the context

@@ -359,9 +359,25 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
     if (getenv("QCP2_CCSD_NO_PERM_CACHE")) ctx.perm_cache = nullptr;
     fill_zero(ctx, T1, O * V);                                                             // :417-419
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
-    cudaEvent_t ev0, ev1;
-    QCP2_CUDA(cudaEventCreate(&ev0));
-    QCP2_CUDA(cudaEventCreate(&ev1));
+    // events and the graph executable are released on every exit path (a throw from the body -- e.g. out of memory in a
+    // workspace allocation at large v -- must not leak them)
+    struct LoopResources {
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t stream;
+        explicit LoopResources(cudaStream_t s) : stream(s) {}
+        ~LoopResources() {
+            if (exec) {
+                cudaStreamSynchronize(stream);
+                cudaGraphExecDestroy(exec);
+            }
+            if (ev0) cudaEventDestroy(ev0);
+            if (ev1) cudaEventDestroy(ev1);
+        }
+    } res(ctx.stream);
+    QCP2_CUDA(cudaEventCreate(&res.ev0));
+    QCP2_CUDA(cudaEventCreate(&res.ev1));
+    cudaEvent_t &ev0 = res.ev0, &ev1 = res.ev1;
     QCP2_CUDA(cudaEventRecord(ev0, ctx.stream));
     double e_last = 0.0, e = 0.0;
     int it = 0;
@@ -457,7 +473,7 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
         ctx.sync();// sol is pageable
     };
     bool use_graph = getenv("QCP2_CCSD_NO_GRAPH") == nullptr && ctx.shard == nullptr;// (NCCL calls stay outside graphs)
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t &graph_exec = res.exec;
     long long graph_launches = 0;
     for (; it < maxiter; ++it) {
         ccsd_energy(ctx, T1, T2, I.p[I_OOVV], fov, o, v, e_dev);                           // :432
@@ -504,18 +520,12 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
         ctx.launches += graph_launches;
         diis_after();
     }
-    if (graph_exec) {
-        cudaStreamSynchronize(ctx.stream);
-        cudaGraphExecDestroy(graph_exec);
-    }
     QCP2_CUDA(cudaEventRecord(ev1, ctx.stream));
     QCP2_CUDA(cudaEventSynchronize(ev1));
     tr.mark("iteration loop");
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     ctx.ccsd_loop_seconds = ms * 1e-3;
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     *e_host = e;
     if (iters_host) *iters_host = it;
 }

@@ -109,9 +109,16 @@ __global__ void __launch_bounds__(THREADS, 1) t_gemm_tma_kernel(const TmaGemmArg
                 mbar_wait(&empty[stage], phase);
                 mbar_expect_tx(&full[stage], (uint32_t) A_BYTES + (uint32_t) rows * rowbytes);
                 bulk_g2s(As + stage * A_STAGE, Asrc + (long long) kb * A_STAGE, A_BYTES, &full[stage]);
-                const double *brow = sd.B[s] + (long long) lk0 * g.seg_ldb[s] + n0;
                 double *bdst = Bs + stage * B_STAGE;
-                for (int r = 0; r < rows; ++r) bulk_g2s(bdst + r * BLD, brow + (long long) r * g.seg_ldb[s], rowbytes, &full[stage]);
+                if (s == 3 && g.merged_sub_rows > 0) {// merged hole block: row lk0 + r lives in sub-segment (lk0 + r) / o
+                    for (int r = 0; r < rows; ++r) {
+                        const int lr = lk0 + r, sub = lr / g.merged_sub_rows, loc = lr - sub * g.merged_sub_rows;
+                        bulk_g2s(bdst + r * BLD, sd.B[3 + sub] + (long long) loc * g.seg_ldb[3] + n0, rowbytes, &full[stage]);
+                    }
+                } else {
+                    const double *brow = sd.B[s] + (long long) lk0 * g.seg_ldb[s] + n0;
+                    for (int r = 0; r < rows; ++r) bulk_g2s(bdst + r * BLD, brow + (long long) r * g.seg_ldb[s], rowbytes, &full[stage]);
+                }
                 if (++stage == S) stage = 0, phase ^= 1u;
             }
         }

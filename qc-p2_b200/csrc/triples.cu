@@ -93,6 +93,7 @@ struct BuildAArgs {
     double *A;
     int o, v, kpad, count;
     int tiled, mtiles;// tiled: A[t][m-tile][k-block][TG_BM][TG_ALD] (the TMA kernel's stage image)
+    int merged;       // the three o-row (hole) segments form ONE block of 3 o rows behind segment 3 (K padded once, not three times)
     int kb_begin[GEMM_MAX_SEG + 1];
 };
 
@@ -128,7 +129,12 @@ __global__ void build_A_kernel(BuildAArgs p) {
 #pragma unroll
         for (int q = 1; q < GEMM_MAX_SEG; ++q)
             if (col >= p.kb_begin[q] * GEMM_BK) s = q;
-        const long long r = col - p.kb_begin[s] * GEMM_BK;
+        long long r = col - p.kb_begin[s] * GEMM_BK;
+        if (p.merged && s >= 3) {// row r of the merged hole block belongs to sub-segment r / o
+            s = 3 + (int) (r / O);
+            r -= (long long) (s - 3) * O;
+            if (s > 5) s = 5, r = O;// padding rows
+        }
         double val = 0.0;
         if (s < 3) {
             if (r < V) {
@@ -461,8 +467,15 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
     P->eo = DBuf(ctx, (size_t) o), P->ev = DBuf(ctx, (size_t) v);
     QCP2_CUDA(cudaMemcpyAsync(P->eo.p, eps_o, (size_t) o * 8, cudaMemcpyDeviceToDevice, ctx.stream));
     QCP2_CUDA(cudaMemcpyAsync(P->ev.p, eps_v, (size_t) v * 8, cudaMemcpyDeviceToDevice, ctx.stream));
-    for (int s = 0; s < GEMM_MAX_SEG; ++s)
-        P->kb_begin[s + 1] = P->kb_begin[s] + (int) (((s < 3 ? V : O) + GEMM_BK - 1) / GEMM_BK);
+    {
+        const char *env = getenv("QCP2_T_GEMM");// "cpasync" forces the non-TMA kernel (A/B experiments)
+        P->merged_o = !(env && std::string(env) == "cpasync");// the TMA kernel fetches B row by row, so the three hole segments
+    }                                                          // (o rows each) can share one padded block: K pad 3 x (16 - o % 16) -> once
+    for (int s = 0; s < GEMM_MAX_SEG; ++s) {
+        long long rows = s < 3 ? V : O;
+        if (P->merged_o && s >= 3) rows = s == 3 ? 3 * O : 0;
+        P->kb_begin[s + 1] = P->kb_begin[s] + (int) ((rows + GEMM_BK - 1) / GEMM_BK);
+    }
     P->kpad = P->kb_begin[GEMM_MAX_SEG] * GEMM_BK;
     if (P->ncols > 0) {
         // Both modes own re-laid copies [i][e][ld] / [i][m][ld] of <vo||vv> and T2 (symmetric: b<c packed; literal: all
@@ -573,6 +586,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
         const bool want_tma = !(env && std::string(env) == "cpasync");
         const bool rows_aligned = ((reinterpret_cast<uintptr_t>(P->vovvP.p) & 15) == 0) && ((reinterpret_cast<uintptr_t>(P->T2P.p) & 15) == 0);
         P->use_tma = want_tma && rows_aligned && P->ncols > 0;// both modes; the cp.async SEG kernel stays as an A/B option
+        QCP2_REQUIRE(P->use_tma == P->merged_o || P->ncols == 0, "(T): packed rows are not 16-byte aligned");
         const long long mtiles = (V + TG_BM - 1) / TG_BM;
         P->a_per_triple = P->use_tma ? mtiles * (P->kpad / GEMM_BK) * TG_BM * TG_ALD : V * P->kpad;
     }
@@ -710,7 +724,7 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         BuildAArgs ba;
         ba.T2 = P.T2, ba.ovoo = P.ovoo, ba.ijk = P.ijk_dev + 3 * off, ba.A = P.Abuf[s];
         ba.o = P.o, ba.v = P.v, ba.kpad = P.kpad, ba.count = cnt;
-        ba.tiled = P.use_tma ? 1 : 0, ba.mtiles = (P.v + TG_BM - 1) / TG_BM;
+        ba.tiled = P.use_tma ? 1 : 0, ba.mtiles = (P.v + TG_BM - 1) / TG_BM, ba.merged = P.merged_o ? 1 : 0;
         for (int q = 0; q <= GEMM_MAX_SEG; ++q) ba.kb_begin[q] = P.kb_begin[q];
         build_A_kernel<<<grid_for((long long) cnt * P.a_per_triple, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(ba);
         ctx.launched("build_A");
@@ -724,6 +738,7 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
             g.seg = P.seg_dev + off, g.nseg = GEMM_MAX_SEG;
             for (int q = 0; q <= GEMM_MAX_SEG; ++q) g.seg_kb_begin[q] = P.kb_begin[q];
             for (int q = 0; q < GEMM_MAX_SEG; ++q) g.seg_rows[q] = q < 3 ? P.v : P.o, g.seg_ldb[q] = nc;
+            if (P.merged_o) g.seg_rows[3] = 3 * P.o, g.seg_rows[4] = g.seg_rows[5] = 0, g.merged_sub_rows = P.o;
             launch_t_gemm_tma(ctx, g, cnt);
         } else {
             GemmArgs g;

@@ -22,6 +22,7 @@ struct TmaGemmArgs {
     int seg_kb_begin[GEMM_MAX_SEG + 1] = {0, 0, 0, 0, 0, 0, 0};
     int seg_rows[GEMM_MAX_SEG] = {0, 0, 0, 0, 0, 0};
     long long seg_ldb[GEMM_MAX_SEG] = {0, 0, 0, 0, 0, 0};
+    int merged_sub_rows = 0;     // > 0: segment 3 is the merged hole block, rows [q s, (q+1) s) come from seg->B[3 + q]
 };
 void launch_t_gemm_tma(Ctx &ctx, const TmaGemmArgs &g, int batch);
 
@@ -59,6 +60,7 @@ struct TPlan {
     std::vector<cudaEvent_t> slab_ready;  // one per occupied index
     DBuf stage;
     unsigned long long *vovv_defect = nullptr;// device [2]: max |x[e,b,c] + x[e,c,b]|, max |x| over the slabs
+    bool merged_o = false;          // the three hole segments share one padded K block (TMA kernel only)
     bool use_tma = false;           // the TMA/mbarrier kernel (t_gemm_tma.cu) runs the triples GEMM (both modes)
     long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
     ~TPlan();

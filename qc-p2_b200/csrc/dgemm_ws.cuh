@@ -24,6 +24,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "common.cuh"
@@ -46,6 +47,8 @@ struct WsGemmArgs {
     const long long *row_off = nullptr;    // optional offset tables: address = C + row_off[m] + col_off[n]
     const long long *col_off = nullptr;
     int k_splits = 1, kb_per_split = 0;
+    int tiles = 0;                         // M-tiles x N-tiles; the grid is persistent: CTA b works on items b, b + gridDim.x, ...
+    long long work = 0;                    // of the tiles x k_splits x batch work items (tile fastest)
     double2 *ws = nullptr;                 // split-K partials, [batch][tile][split][frag][256 threads]
     unsigned int *counters = nullptr;      // one per (batch, tile); zero before and after the launch
 };
@@ -124,12 +127,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles_m = (g.M + BM - 1) / BM;
-    const int tile = blockIdx.x;
-    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-    const int bz = blockIdx.z;
     const int nkb_total = (g.K + BK - 1) / BK;
-    const int kb0 = g.k_splits > 1 ? (int) blockIdx.y * g.kb_per_split : 0;
-    const int nkb = g.k_splits > 1 ? max(0, min(nkb_total, kb0 + g.kb_per_split) - kb0) : nkb_total;
+    // work item w -> (tile, split, batch member); both roles walk the same sequence w = blockIdx.x, + gridDim.x, ...
+    // The mbarrier ring runs on across items, so the producer is already fetching the next item's first stages while
+    // the consumers are in the epilogue of the current one.
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
@@ -146,30 +147,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         if (warp == WS_NCW && lane == 0) {
             asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
             asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
-            const int za = g.a_batched ? bz : 0, zb = g.b_batched ? bz : 0;
-            // boxes that lie entirely past the M / N edge are not fetched: their rows of the tile only feed
-            // accumulator rows / columns that are never stored
-            const int a_boxes = A_KC ? 1 : min(BM / 16, (g.M - m0 + 15) / 16);
-            const int b_boxes = B_NC ? min(BN / 16, (g.N - n0 + 15) / 16) : 1;
-            const uint32_t bytes = (uint32_t) ((A_KC ? A_STAGE : a_boxes * 256) + (B_NC ? b_boxes * 256 : B_STAGE)) * 8u;
             int stage = 0;
             uint32_t phase = 1;// fresh barriers: waiting on the preceding phase returns at once
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int k0 = (kb0 + kb) * BK;
-                mbar_wait(&empty[stage], phase);
-                mbar_expect_tx(&full[stage], bytes);
-                double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
-                if (A_KC) {
-                    tma_load_3d(as, &tmA, k0, m0, za, &full[stage]);
-                } else {
-                    for (int b = 0; b < a_boxes; ++b) tma_load_3d(as + b * 256, &tmA, m0 + 16 * b, k0, za, &full[stage]);
+            for (long long w = blockIdx.x; w < g.work; w += gridDim.x) {
+                const int tile = (int) (w % g.tiles), split = (int) ((w / g.tiles) % g.k_splits), bz = (int) (w / ((long long) g.tiles * g.k_splits));
+                const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+                const int kb0 = g.k_splits > 1 ? split * g.kb_per_split : 0;
+                const int nkb = g.k_splits > 1 ? max(0, min(nkb_total, kb0 + g.kb_per_split) - kb0) : nkb_total;
+                const int za = g.a_batched ? bz : 0, zb = g.b_batched ? bz : 0;
+                // boxes that lie entirely past the M / N edge are not fetched: their rows of the tile only feed
+                // accumulator rows / columns that are never stored
+                const int a_boxes = A_KC ? 1 : min(BM / 16, (g.M - m0 + 15) / 16);
+                const int b_boxes = B_NC ? min(BN / 16, (g.N - n0 + 15) / 16) : 1;
+                const uint32_t bytes = (uint32_t) ((A_KC ? A_STAGE : a_boxes * 256) + (B_NC ? b_boxes * 256 : B_STAGE)) * 8u;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int k0 = (kb0 + kb) * BK;
+                    mbar_wait(&empty[stage], phase);
+                    mbar_expect_tx(&full[stage], bytes);
+                    double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
+                    if (A_KC) {
+                        tma_load_3d(as, &tmA, k0, m0, za, &full[stage]);
+                    } else {
+                        for (int b = 0; b < a_boxes; ++b) tma_load_3d(as + b * 256, &tmA, m0 + 16 * b, k0, za, &full[stage]);
+                    }
+                    if (B_NC) {
+                        for (int b = 0; b < b_boxes; ++b) tma_load_3d(bs + b * 256, &tmB, n0 + 16 * b, k0, zb, &full[stage]);
+                    } else {
+                        tma_load_3d(bs, &tmB, k0, n0, zb, &full[stage]);
+                    }
+                    if (++stage == S) stage = 0, phase ^= 1u;
                 }
-                if (B_NC) {
-                    for (int b = 0; b < b_boxes; ++b) tma_load_3d(bs + b * 256, &tmB, n0 + 16 * b, k0, zb, &full[stage]);
-                } else {
-                    tma_load_3d(bs, &tmB, k0, n0, zb, &full[stage]);
-                }
-                if (++stage == S) stage = 0, phase ^= 1u;
             }
         }
         return;
@@ -204,10 +211,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     auto b_frag = [&](int j) -> int { return !B_NC ? j * NWN * 128 : j * (NWN / 2) * 256; };
 
     double acc[FM][FN][2];
-#pragma unroll
-    for (int i = 0; i < FM; ++i)
-#pragma unroll
-        for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     double fa[2][FM], fb[2][FN];
     auto ldfrag = [&](int buf, int stage, int ks) {
         const double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
@@ -220,11 +223,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int j = 0; j < FN; ++j) fb[buf][j] = bs[b_off[ks] + b_frag(j)];
     };
 
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long w = blockIdx.x; w < g.work; w += gridDim.x) {
+    const int tile = (int) (w % g.tiles), split = (int) ((w / g.tiles) % g.k_splits), bz = (int) (w / ((long long) g.tiles * g.k_splits));
+    const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+    const int kb0 = g.k_splits > 1 ? split * g.kb_per_split : 0;
+    const int nkb = g.k_splits > 1 ? max(0, min(nkb_total, kb0 + g.kb_per_split) - kb0) : nkb_total;
+#pragma unroll
+    for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     if (nkb > 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        mbar_wait(&full[0], 0);
-        ldfrag(0, 0, 0);
+        mbar_wait(&full[stage], phase);
+        ldfrag(0, stage, 0);
         for (int kb = 0; kb < nkb; ++kb) {
             int nstage = stage + 1;
             uint32_t nphase = phase;
@@ -251,8 +263,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     // ---- split-K: publish the partial tile; only the last CTA of this tile continues into the epilogue.
     // Fragments that lie entirely past the M / N edge (most of a skinny tile) are neither published nor reduced.
     if (g.k_splits > 1) {
-        const long long slot = ((long long) bz * gridDim.x + tile) * g.k_splits;
-        double2 *mine = g.ws + (slot + blockIdx.y) * (FM * FN * 256) + tid;
+        const long long slot = ((long long) bz * g.tiles + tile) * g.k_splits;
+        double2 *mine = g.ws + (slot + split) * (FM * FN * 256) + tid;
         bool live[FM][FN];
 #pragma unroll
         for (int i = 0; i < FM; ++i)
@@ -264,11 +276,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         __threadfence();
         consumer_bar();
         if (tid == 0) {
-            const unsigned int old = atomicAdd(&g.counters[(long long) bz * gridDim.x + tile], 1u);
+            const unsigned int old = atomicAdd(&g.counters[(long long) bz * g.tiles + tile], 1u);
             *flag = old;
         }
         consumer_bar();
-        if (*flag != (unsigned int) g.k_splits - 1) return;
+        const bool last = *flag == (unsigned int) g.k_splits - 1;
+        consumer_bar();// every consumer has read the flag before a later item may overwrite it
+        if (!last) continue;
         __threadfence();
         const double2 *all = g.ws + slot * (FM * FN * 256) + tid;
         constexpr long long SPLIT_STRIDE = (long long) FM * FN * 256;
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                     acc[i][j][0] = s0, acc[i][j][1] = s1;
                 }
         }
-        if (tid == 0) g.counters[(long long) bz * gridDim.x + tile] = 0u;// ready for the next launch
+        if (tid == 0) g.counters[(long long) bz * g.tiles + tile] = 0u;// ready for the next launch
     }
 
     // ---- epilogue: C = alpha*acc + beta*Cin
@@ -376,6 +390,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             }
         }
     }
+    }// work items
 }
 
 // ---- host side --------------------------------------------------------------------------
@@ -393,10 +408,12 @@ void ws_launch_inst(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, co
         configured[ctx.device & 63] = true;
     }
     const long long tiles = (long long) ((g.M + Sh::BM - 1) / Sh::BM) * ((g.N + Sh::BN - 1) / Sh::BN);
-    QCP2_REQUIRE(tiles > 0 && tiles < (1LL << 31) && g.batch >= 1 && g.batch <= 65535 && g.k_splits >= 1 && g.k_splits <= 65535,
-                 "ws_dgemm: grid out of range");
-    dim3 grid((unsigned) tiles, (unsigned) g.k_splits, (unsigned) g.batch);
-    kern<<<grid, WS_THREADS, Sh::SMEM, ctx.stream>>>(tmA, tmB, g);
+    QCP2_REQUIRE(tiles > 0 && tiles < (1LL << 31) && g.batch >= 1 && g.k_splits >= 1, "ws_dgemm: grid out of range");
+    WsGemmArgs a = g;
+    a.tiles = (int) tiles, a.work = tiles * g.k_splits * g.batch;
+    // persistent grid: one CTA per SM (the ring takes the SM's shared memory), each walking the work items with stride gridDim.x
+    const unsigned grid = (unsigned) std::min<long long>(a.work, ctx.sm_count);
+    kern<<<grid, WS_THREADS, Sh::SMEM, ctx.stream>>>(tmA, tmB, a);
     ctx.launched("ws_dgemm");
 }
 

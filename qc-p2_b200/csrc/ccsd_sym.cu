@@ -11,7 +11,7 @@
 //    row-concatenated operand [<ab||ef>; <am||ef>; <mn||ef>] plus three small products;
 //  * the t1.t1 parts of W_mbej (cc.cpp:249) and of the ring terms (cc.cpp:360-363) are contracted one t1 at a time
 //    (2 o^3 v^2 flops each instead of an (ov)^3 product);
-//  * W_mbej is held as [m,e,b,j], the order its only consumer reads in place; results whose index order interleaves the
+//  * W_mbej is held as [m,e,j,b], the order its only consumer reads in place; results whose index order interleaves the
 //    free indices of the two operands are written through the GEMM's offset-table epilogue (no re-layout pass);
 //  * where a contraction wants T2 or tau-bar with the LAST index free, the antisymmetry t[..,a,f] = -t[..,f,a] supplies
 //    that order for free (cc.cpp:196, :277);
@@ -176,10 +176,10 @@ bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, const double 
         pack_pairs(ctx, I.p[I_OOVV], o, v, k.alls, k.nall, k.oovvA.p, k.ldk, cm);
         k.tauoP = DBuf(ctx, (size_t) (std::max(k.nrow, 1) * k.ldk));
     }
-    sp.ovvo_mebj = DBuf(ctx, (size_t) (O * V * V * O));
+    sp.ovvo_mejb = DBuf(ctx, (size_t) (O * V * V * O));
     {
-        const long long ext[4] = {O, V, V, O}, istr[4] = {V * V * O, O, V * O, 1};// <mb||ej> read as [m,e,b,j]
-        permute_axpby(ctx, sp.ovvo_mebj.p, I.p[I_OVVO], 4, ext, istr, 1.0, 0.0);
+        const long long ext[4] = {O, V, O, V}, istr[4] = {V * V * O, O, 1, V * O};// <mb||ej> read as [m,e,j,b]
+        permute_axpby(ctx, sp.ovvo_mejb.p, I.p[I_OVVO], 4, ext, istr, 1.0, 0.0);
     }
     tr.mark(blocked ? "pack <vv||vv>, <vo||vv>, <oo||vv> to pairs, one block per spin class" : "pack <vv||vv>, <vo||vv>, <oo||vv> to pairs");
     return true;
@@ -227,7 +227,7 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     // ---------------------------------------------------------------- intermediates, cc.cpp:175-255 (Stanton eqs. 3-8)
     DBuf fae(ctx, (size_t) (V * V)), fmi(ctx, (size_t) (O * O)), fme(ctx, (size_t) (O * V)), wmnij(ctx, (size_t) (O * O * O * O)),
             wm(ctx, (size_t) o2v2);
-    const TView Fae(fae.p, {V, V}), Fmi(fmi.p, {O, O}), Fme(fme.p, {O, V}), Wmnij(wmnij.p, {O, O, O, O}), Wm(wm.p, {O, V, V, O});
+    const TView Fae(fae.p, {V, V}), Fmi(fmi.p, {O, O}), Fme(fme.p, {O, V}), Wmnij(wmnij.p, {O, O, O, O}), Wm(wm.p, {O, V, O, V});
     fill_zero(ctx, fae.p, V * V);
     if (fov) contract(ctx, -0.5, TView(fov, {O, V}), "me", ts, "ma", 1.0, Fae, "ae");          // :194
     contract(ctx, 1.0, ts, "mf", ovvv, "mafe", 1.0, Fae, "ae");                                // :195
@@ -268,19 +268,19 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
         gemm(ctx, g, true, false);
         wmnij_unpack_add(ctx, yo, k.ldo, o, k.rows, k.nrow, 0.5, wmnij.p);
     }
-    {// W_mbej as [m,e,b,j]
-        contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 1.0, Wm, "mebj", sp.ovvo_mebj.p);           // :245 + :250
+    {// W_mbej as [m,e,j,b]
+        contract(ctx, 1.0, ts, "jf", ovvv, "mbef", 1.0, Wm, "mejb", sp.ovvo_mejb.p);           // :245 + :250
         DBuf p2(ctx, (size_t) (O * O * V * O));
         const TView P2(p2.p, {O, O, V, O});
         contract(ctx, 1.0, ts, "jf", oovv, "mnef", 1.0, P2, "mnej", I.p[I_OOVO]);              // <mn||ej> + sum_f t_jf <mn||ef>
-        contract(ctx, -1.0, ts, "nb", P2, "mnej", 1.0, Wm, "mebj");                            // :246 + the t.t part of :249
+        contract(ctx, -1.0, ts, "nb", P2, "mnej", 1.0, Wm, "mejb");                            // :246 + the t.t part of :249
         if (!ring_blocks) {
-            contract(ctx, 1.0, TView(tt.p, {O, V, O, V}), "jbnf", oovv, "mnef", 1.0, Wm, "mebj");// :247
+            contract(ctx, 1.0, TView(tt.p, {O, V, O, V}), "jbnf", oovv, "mnef", 1.0, Wm, "mejb");// :247
         } else {
             // :247 per spin block: C[(j,b) r][(m,e) c] = ttS[r][k] . <mn||ef>S[k][c], added into W[(m,e)][(j,b)] (transposed store)
             fill_zero(ctx, wS.p, ldr * ldr);
-            const long long wd[4] = {O, V, V, O};
-            ov_sort4(ctx, wm.p, wd, /*row (m,e)*/ 0, 1, /*col (j,b)*/ 3, 2, v, sp.ovpos, ldr, 1.0, wS.p);
+            const long long wd[4] = {O, V, O, V};
+            ov_sort4(ctx, wm.p, wd, /*row (m,e)*/ 0, 1, /*col (j,b)*/ 2, 3, v, sp.ovpos, ldr, 1.0, wS.p);
             static const int rkc[3][3] = {{0, 0, 0}, {1, 2, 1}, {2, 1, 2}};
             for (int q = 0; q < 3; ++q) {
                 const int r = rkc[q][0], kk = rkc[q][1], c = rkc[q][2];
@@ -364,11 +364,11 @@ void ccsd_sym_iteration(Ctx &ctx, const IntsDev &I, const double *foo, const dou
     }
     // ring terms cc.cpp:354-363: Rt[i,a,b,j] = sum_me t_imae W_mbej + sum_m t_ma (sum_e t_ie <mb||je>), used at four relabelings
     DBuf rt(ctx, (size_t) o2v2), p1(ctx, (size_t) (O * O * V * O));
-    const TView Rt(rt.p, {O, V, V, O}), P1(p1.p, {O, O, V, O});
-    contract(ctx, 1.0, tn, "ie", ovov, "mbje", 0.0, P1, "imbj");
-    contract(ctx, 1.0, tn, "ma", P1, "imbj", 0.0, Rt, "iabj");                                 // :360-363 (first writer)
+    const TView Rt(rt.p, {O, V, O, V}), P1(p1.p, {O, O, O, V});
+    contract(ctx, 1.0, tn, "ie", ovov, "mbje", 0.0, P1, "imjb");
+    contract(ctx, 1.0, tn, "ma", P1, "imjb", 0.0, Rt, "iajb");                                 // :360-363 (first writer)
     if (!ring_blocks) {
-        contract(ctx, 1.0, Lf, "iame", Wm, "mebj", 1.0, Rt, "iabj");                           // :354-357
+        contract(ctx, 1.0, Lf, "iame", Wm, "mejb", 1.0, Rt, "iajb");                           // :354-357
     } else {
         static const int rkc[3][3] = {{0, 0, 0}, {1, 2, 2}, {2, 1, 1}};// (class of (i,a), of (m,e), of (j,b))
         for (int q = 0; q < 3; ++q) {

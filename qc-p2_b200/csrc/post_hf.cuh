@@ -22,7 +22,7 @@ struct SoSource {
 // exact zeros) a pair (x,y) belongs to class s_x + s_y (0 = alpha-alpha, 1 = mixed, 2 = beta-beta) and every pair-packed
 // matrix is block diagonal in the class: only the diagonal blocks are stored and multiplied.
 struct SymPack {
-    DBuf ints_buf, ovvo_mebj;
+    DBuf ints_buf, ovvo_mejb;
     int ncls = 1;
     bool spin_blocked = false;
     int npo = 0, npv = 0;

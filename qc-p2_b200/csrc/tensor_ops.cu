@@ -914,7 +914,7 @@ void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, PairColMap 
 }
 
 // The last step of the fused T2 equation (cc.cpp:312-383 assembled in one pass):
-//   r = <ij||ab> + P(ab) Uab + P(ij) Uij + P(ij)P(ab) Rt[i,a,b,j] + s(ij) s(ab) LP[i<j][a<b];   T2_new = r / D_ijab
+//   r = <ij||ab> + P(ab) Uab + P(ij) Uij + P(ij)P(ab) Rt[i,a,j,b] + s(ij) s(ab) LP[i<j][a<b];   T2_new = r / D_ijab
 __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double *__restrict__ Uab, const double *__restrict__ Uij,
                                    const double *__restrict__ Rt, const double *__restrict__ RtS, const int *__restrict__ ovpos, long long ldr,
                                    LadderBlocks lb,
@@ -931,7 +931,7 @@ __global__ void finalize_t2_kernel(const double *__restrict__ oovv, const double
         const int i = (int) (q / o);
         const long long ijba = ((long long) i * o + j) * vv + (long long) b * v + a;
         const long long jiab = ((long long) j * o + i) * vv + (long long) a * v + b;
-        auto at = [&](int x, int c, int d, int y) { return Rt[(((long long) x * v + c) * v + d) * o + y]; };
+        auto at = [&](int x, int c, int d, int y) { return Rt[(((long long) x * v + c) * o + y) * v + d]; };// Rt[i,a,j,b] at (i,a,b,j)
         double x = oovv[lin] + (Uab[lin] - Uab[ijba]) + (Uij[lin] - Uij[jiab]);
         x += at(i, a, b, j) - at(j, a, b, i) - at(i, b, a, j) + at(j, b, a, i);
         if (RtS) {// the (ov)^3 part of the ring terms, held as a matrix over class-sorted (i,a) x (j,b) composites

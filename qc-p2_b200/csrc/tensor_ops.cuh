@@ -78,7 +78,7 @@ void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, do
 void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,
               bool bar = false, PairColMap cm = PairColMap());// rows = any list of (i,j) pairs; bar: tau-bar (Stanton eq. 10)
 void pair_trace_add(Ctx &ctx, const double *G, long long ldg, int o, PairColMap all, double *F);
-// Rt: [i,a,b,j]; RtS (may be null): matrix [pos(i,a)][pos(j,b)] with row stride ldr over class-sorted composites
+// Rt: [i,a,j,b]; RtS (may be null): matrix [pos(i,a)][pos(j,b)] with row stride ldr over class-sorted composites
 void ov_sort4(Ctx &ctx, const double *src, const long long d[4], int ro, int rv, int co, int cv, int V, const int *pos, long long ld,
               double alpha, double *out);
 void finalize_t2(Ctx &ctx, const double *oovv, const double *Uab, const double *Uij, const double *Rt, const double *RtS,

@@ -123,6 +123,10 @@ def test_config3_ch4_ccpvtz_fused_pipeline_vs_committed_cpu_oracle(ctx):
     assert abs(r["e_mp2"] - g["e_mp2"]) < E_TOL and abs(r["e_ccsd"] - g["e_ccsd"]) < E_TOL and abs(r["e_t"] - g["e_t"]) < E_TOL
     assert r["iters"] == g["iters"] and np.max(np.abs(r["e_hist"] - np.array(g["e_hist"]))) < E_TOL
     assert ctx.ccsd_last_mode() == 2
+    # ... and against the reference's OWN MP2() / CCSD() on this config (tests/golden/make_reference_golden_ch4.py: 37 minutes
+    # of the reference's code on the shim's OpenMP GEMM; its CCSD_T() cannot hold 4 x o^3 v^3 = 136 GB)
+    gr = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_energies.json")))["ch4_ccpvtz_rhf"]
+    assert abs(r["e_mp2"] - gr["e_mp2"]) < E_TOL and abs(r["e_ccsd"] - gr["e_ccsd"]) < E_TOL and r["iters"] == gr["cc_iters"]
     # the same solve with the spin classes switched off (one class, dense pairs): identical trajectory to rounding
     os.environ["QCP2_CCSD_NO_SPIN_BLOCKS"] = "1"
     try:

@@ -79,3 +79,18 @@ def test_scf_energy_is_rotation_invariant(tmp_path):
         xyz.write_text("3\n\n" + "\n".join("%s %.12f %.12f %.12f" % (s, *p) for s, p in zip("OHH", pts)) + "\n")
         es.append(hs.scf(str(xyz), "cc-pvdz", conv=1e-11)["e_scf"])
     assert abs(es[0] - es[1]) < 1e-9
+
+
+def test_config3_oracle_golden_equals_the_reference_s_own_mp2_and_ccsd():
+    """CH4/cc-pVTZ: the committed CPU-oracle numbers (tests/golden/ch4_ccpvtz_oracle.json) against the reference's OWN MP2() /
+    CCSD() run on the same molecule (tests/golden/reference_energies.json, entry written by make_reference_golden_ch4.py --
+    37 minutes of the reference's unmodified sources on the shim's OpenMP GEMM).  CCSD_T() cannot hold this config."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    orc_g = json.load(open(os.path.join(root, "tests", "golden", "ch4_ccpvtz_oracle.json")))
+    ref_g = json.load(open(os.path.join(root, "tests", "golden", "reference_energies.json")))["ch4_ccpvtz_rhf"]
+    assert (ref_g["n"], ref_g["no"], ref_g["nv"]) == (86, 10, 162)
+    assert abs(orc_g["e_scf"] - ref_g["e_scf"]) < 1e-9
+    assert abs(orc_g["e_mp2"] - ref_g["e_mp2"]) < 1e-10 and abs(orc_g["e_ccsd"] - ref_g["e_ccsd"]) < 1e-10
+    assert orc_g["iters"] == ref_g["cc_iters"] == 29

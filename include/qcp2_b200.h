@@ -240,6 +240,12 @@ long long qcp2_gemm_log_read(const qcp2_ctx *ctx, long long *recs, long long cap
  * the spatial MO tensors (integrals.cpp:136-167 + 184-207 fused; bit-identical values).  out has the block's extents. */
 int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const double *ab, int n, int o, int v, const char *spec,
                   double *out);
+/* Amplitude restart (opt-in).  The reference's CCSD() always starts from T1 = 0 and the MP2 doubles
+ * (cc.cpp:417-421).  A host that has saved the T1 / T2 a previous qcp2_ccsd / qcp2_post_hf returned can resume: pass the saved
+ * T2 as `T2_guess` and register the saved T1 here (host or device pointer per the pointer mode; copied); the NEXT CCSD solve
+ * of this context starts from it, after which the setting is cleared.  T1 == NULL cancels.  `P2` does this with
+ * QCP2_AMPLITUDES=<file>: it resumes from the file if it matches (o, v) and rewrites it after the solve. */
+int qcp2_ccsd_set_start_T1(qcp2_ctx *ctx, const double *T1, int o, int v);
 /* Opt-in DIIS for the CCSD loops of this context (qcp2_ccsd, qcp2_post_hf*): nvec = 0 (default) is the reference's plain
  * Jacobi iteration (cc.cpp:426-447: same trajectory, same iteration count); 2..12 extrapolates over the last nvec Jacobi
  * steps (Pulay; error vector = amplitude change).  Same fixed point, fewer iterations.  The environment variable

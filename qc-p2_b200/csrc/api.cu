@@ -20,6 +20,7 @@ using namespace qcp2;
 
 struct qcp2_ctx {
     Ctx c;
+    DBuf t1_start;// qcp2_ccsd_set_start_T1: consumed by the next CCSD solve
     Comm *comm = nullptr;// NCCL communicator (qcp2_comm_init); null = single GPU
     bool ccsd_sharding = false;// qcp2_set_ccsd_sharding: qcp2_ccsd is collective and splits its large products
 };
@@ -148,6 +149,7 @@ int qcp2_destroy(qcp2_ctx *ctx) {
         }
         ctx->comm = nullptr;
     }
+    ctx->t1_start.reset();
     if (ctx->c.ws_counters) cudaFree(ctx->c.ws_counters);
     for (Ctx::OffsetTable &t : ctx->c.offset_tables) cudaFree(t.dev);
     if (ctx->c.pool) {
@@ -1061,6 +1063,21 @@ int qcp2_so_block(qcp2_ctx *ctx, const double *aa, const double *bb, const doubl
         so_block(c, a, b, m, n, o, v, spec, res);
         res.finish();
         c.sync();
+    });
+}
+
+int qcp2_ccsd_set_start_T1(qcp2_ctx *ctx, const double *T1, int o, int v) {
+    return guarded(ctx, [&](Ctx &c) {
+        QCP2_REQUIRE(o >= 0 && v >= 0, "ccsd_set_start_T1: negative extent");
+        c.ccsd_t1_start = nullptr;
+        ctx->t1_start.reset();
+        if (!T1) return;
+        const long long n = (long long) o * v;
+        ctx->t1_start = DBuf(c, (size_t) std::max<long long>(n, 1));
+        QCP2_CUDA(cudaMemcpyAsync(ctx->t1_start.p, T1, (size_t) n * 8,
+                                  c.pointer_mode == QCP2_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+        c.sync();
+        c.ccsd_t1_start = ctx->t1_start.p;
     });
 }
 

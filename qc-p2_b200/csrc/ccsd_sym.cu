@@ -81,6 +81,11 @@ bool sym_setup(Ctx &ctx, const IntsDev &I, const double *T2_guess, const double 
             const int off[4] = {0, 0, 0, o};
             spin_pattern_defect_async(ctx, fov, d, off, chk + 20 + nspin++);
         }
+        if (ctx.ccsd_t1_start) {// a restart T1 must be spin-diagonal as well
+            const long long d[4] = {1, O, 1, V};
+            const int off[4] = {0, 0, 0, o};
+            spin_pattern_defect_async(ctx, ctx.ccsd_t1_start, d, off, chk + 20 + nspin++);
+        }
         QCP2_REQUIRE(nspin <= 16, "sym_setup: spin check slots");
     }
     unsigned long long h[kSlots];

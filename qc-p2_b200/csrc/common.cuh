@@ -58,6 +58,7 @@ struct Ctx {
     long long launches = 0;
     std::string last_error;
     double ccsd_loop_seconds = 0.0;
+    const double *ccsd_t1_start = nullptr;// one-shot: device T1 the next CCSD loop starts from instead of zero (qcp2_ccsd_set_start_T1)
     int ccsd_diis = 0;      // opt-in DIIS subspace size of the CCSD loop (qcp2_set_ccsd_diis; 0 = the reference's plain Jacobi loop)
     int last_ccsd_mode = -1;// formulation the last CCSD solve used: 0 dense term list, 1 pair-packed, 2 pair-packed + spin classes
     PermCache *perm_cache = nullptr;

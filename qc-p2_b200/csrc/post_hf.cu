@@ -357,7 +357,12 @@ void ccsd_dev(Ctx &ctx, const IntsDev &I_in, const double *foo, const double *fo
         }
     } cache_guard(ctx, perm_cache);
     if (getenv("QCP2_CCSD_NO_PERM_CACHE")) ctx.perm_cache = nullptr;
-    fill_zero(ctx, T1, O * V);                                                             // :417-419
+    if (ctx.ccsd_t1_start) {// restart from checkpointed amplitudes (opt-in; the reference always starts from T1 = 0, :417-419)
+        QCP2_CUDA(cudaMemcpyAsync(T1, ctx.ccsd_t1_start, (size_t) (O * V) * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        ctx.ccsd_t1_start = nullptr;
+    } else {
+        fill_zero(ctx, T1, O * V);                                                         // :417-419
+    }
     QCP2_CUDA(cudaMemcpyAsync(T2, T2_guess, (size_t) o2v2 * 8, cudaMemcpyDeviceToDevice, ctx.stream));// :421
     // events and the graph executable are released on every exit path (a throw from the body -- e.g. out of memory in a
     // workspace allocation at large v -- must not leak them)

@@ -146,7 +146,28 @@ cc_results CCSD(const scf_results &scf, const mp2_results &mp2, const params &co
     std::vector<double> hist((size_t) std::max(config.maxiter, 1), 0.0);
     int iters = 0;
     std::cout << "Starting CCSD Calculations" << std::endl;
-    gpu_check(qcp2_ccsd(gpu(), mp2.so_ints.data(), n2, nullptr, m.F_ii.data(), fov_or_null(m), m.F_aa.data(), mp2.T.data(), o, v,
+    // Optional amplitude checkpoint (not in the reference): QCP2_AMPLITUDES=<file> resumes from the file when its header
+    // matches (o, v) and rewrites it after the solve.  Layout: "QCP2AMP1", int32 o, int32 v, T1[o v], T2[o o v v] doubles.
+    const char *ckpt = getenv("QCP2_AMPLITUDES");
+    DTensor t2_start;
+    const double *t2_guess = mp2.T.data();
+    if (ckpt) {
+        if (FILE *f = fopen(ckpt, "rb")) {
+            char magic[8];
+            int hdr[2] = {0, 0};
+            DTensor t1_start(o, v);
+            t2_start = DTensor(o, o, v, v);
+            const size_t n1 = (size_t) o * v, n2e = n1 * n1;
+            if (fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "QCP2AMP1", 8) == 0 && fread(hdr, 4, 2, f) == 2 && hdr[0] == o && hdr[1] == v &&
+                fread(t1_start.data(), 8, n1, f) == n1 && fread(t2_start.data(), 8, n2e, f) == n2e) {
+                gpu_check(qcp2_ccsd_set_start_T1(gpu(), t1_start.data(), o, v));
+                t2_guess = t2_start.data();
+                std::cout << "Resuming from the amplitudes in " << ckpt << std::endl;
+            }
+            fclose(f);
+        }
+    }
+    gpu_check(qcp2_ccsd(gpu(), mp2.so_ints.data(), n2, nullptr, m.F_ii.data(), fov_or_null(m), m.F_aa.data(), t2_guess, o, v,
                         config.maxiter, config.cc_conv, results.T1.data(), results.T2.data(), &results.ccsd_energy, &iters,
                         hist.data(), blocks));
     std::cout << std::endl << "Iter         E_CC (Eh)        Delta(E_CC)" << std::endl;
@@ -157,6 +178,15 @@ cc_results CCSD(const scf_results &scf, const mp2_results &mp2, const params &co
     }
     if (iters < config.maxiter) std::cout << "CC energy converged" << std::endl;
     results.iterations = iters;
+    if (ckpt) {
+        if (FILE *f = fopen(ckpt, "wb")) {
+            const int hdr[2] = {o, v};
+            const size_t n1 = (size_t) o * v;
+            fwrite("QCP2AMP1", 1, 8, f), fwrite(hdr, 4, 2, f);
+            fwrite(results.T1.data(), 8, n1, f), fwrite(results.T2.data(), 8, n1 * n1, f);
+            fclose(f);
+        }
+    }
     std::cout << std::endl << "CCSD energy: " << results.ccsd_energy << " Eh" << std::endl;
     return results;
 }

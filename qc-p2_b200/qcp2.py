@@ -426,6 +426,14 @@ class Context:
         self.check(self.lib.qcp2_so_block(self.h, _p(aa), _p(bb), _p(ab), aa.shape[0], no, nv, int_string.encode(), _p(out)))
         return out
 
+    def ccsd_set_start_T1(self, T1):
+        """The next CCSD solve starts from this T1 instead of zero (restart from saved amplitudes); None cancels."""
+        if T1 is None:
+            self.check(self.lib.qcp2_ccsd_set_start_T1(self.h, None, 0, 0))
+        else:
+            t = _arr(T1) if isinstance(T1, np.ndarray) else T1
+            self.check(self.lib.qcp2_ccsd_set_start_T1(self.h, _p(t), int(t.shape[0]), int(t.shape[1])))
+
     def set_ccsd_diis(self, nvec):
         """Opt-in DIIS over the last nvec Jacobi steps (0 = the reference's plain Jacobi loop)."""
         self.check(self.lib.qcp2_set_ccsd_diis(self.h, int(nvec)))

@@ -111,6 +111,25 @@ def test_opt_in_diis_reaches_the_same_ccsd_energy_in_fewer_iterations(ctx):
     assert r["iters"] == g["water_ccpvdz_rhf"]["cc_iters"]
 
 
+def test_amplitude_restart_continues_the_same_trajectory(ctx):
+    """Opt-in restart (qcp2_ccsd_set_start_T1 + T2 as the guess): stopping after 10 iterations and resuming must continue the very
+    trajectory of the uninterrupted solve -- same energies from iteration 10 on, same total iteration count."""
+    case = molecule_case(**CONFIGS["water_ccpvdz_rhf"])
+    no, nv = case["no"], case["nv"]
+    e_mp2, so, T2g = ctx.MP2(case["ao"], case["C"], None, case["eps"], case["eps"], no, nv)
+    foo, fov, fvv = fock_blocks(case["eps"], case["eps"], no)
+    full = ctx.CCSD(foo, fov, fvv, T2g, 200, 1e-12, so_ints=so)
+    part = ctx.CCSD(foo, fov, fvv, T2g, 10, 1e-12, so_ints=so)
+    assert part["iters"] == 10
+    ctx.ccsd_set_start_T1(part["T1"])
+    rest = ctx.CCSD(foo, fov, fvv, part["T2"], 200, 1e-12, so_ints=so)
+    assert rest["iters"] == full["iters"] - 10
+    assert np.max(np.abs(rest["e_hist"] - full["e_hist"][10:])) < 1e-13
+    assert abs(rest["ccsd_energy"] - full["ccsd_energy"]) < 1e-13
+    again = ctx.CCSD(foo, fov, fvv, T2g, 200, 1e-12, so_ints=so)      # the setting was one-shot
+    assert again["iters"] == full["iters"]
+
+
 def test_config3_ch4_ccpvtz_fused_pipeline_vs_committed_cpu_oracle(ctx):
     """BASELINE.json config 3 (o=10, v=162): the CPU side takes ~15 min, so its numbers are committed
     (tests/golden/ch4_ccpvtz_oracle.json, generator beside it).  The host SCF is deterministic, so

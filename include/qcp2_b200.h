@@ -223,8 +223,8 @@ int qcp2_contract(qcp2_ctx *ctx, double alpha, const double *A, const long long 
 int qcp2_dgemm(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A,
                long long lda, const double *B, long long ldb, double beta, double *C, long long ldc);
 /* The same product with device pointers only, a strided batch, a forced kernel choice and device timing (tests and
- * tuning tools): tile < 0 lets the library choose; 0..6 force the warp-specialised TMA kernel's CTA tile
- * (80x256, 48x256, 16x256, 64x64, 112x128, 16x192, 32x256), +8 runs the transposed problem C^T = B^T A^T on that tile; k_splits > 0
+ * tuning tools): tile < 0 lets the library choose; 0..7 force the warp-specialised TMA kernel's CTA tile
+ * (80x256, 48x256, 16x256, 64x64, 112x128, 16x192, 32x256, 96x128), +16 runs the transposed problem C^T = B^T A^T on that tile; k_splits > 0
  * forces the split-K factor; the product is launched `reps` times and *seconds (may be NULL) receives the mean device
  * time of one launch.  Operands that are not 16-byte aligned take the cp.async kernel regardless of `tile`. */
 int qcp2_dgemm_ex(qcp2_ctx *ctx, int transA, int transB, int M, int N, int K, double alpha, const double *A, long long lda,

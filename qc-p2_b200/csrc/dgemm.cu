@@ -54,6 +54,7 @@ void ws_dispatch(Ctx &ctx, int shape, const CUtensorMap &ta, const CUtensorMap &
         case WS_64x64: ws_launch_64x64(ctx, ta, tb, w, a_kc, b_nc); break;
         case WS_16x192: ws_launch_16x192(ctx, ta, tb, w, a_kc, b_nc); break;
         case WS_32x256: ws_launch_32x256(ctx, ta, tb, w, a_kc, b_nc); break;
+        case WS_96x128: ws_launch_96x128(ctx, ta, tb, w, a_kc, b_nc); break;
         default: ws_launch_112x128(ctx, ta, tb, w, a_kc, b_nc); break;
     }
 }
@@ -109,7 +110,7 @@ struct WsChoice {
 // fragment-load efficiency, or bound by streaming its operand bytes at the chip's ~3400 B/clk HBM rate shared by the
 // CTAs of a wave), plus the split-K partial traffic
 WsChoice ws_choose(const Ctx &ctx, const GemmArgs &g) {
-    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.85, 0.92, 0.68, 0.80};
+    static const double eff[WS_SHAPE_COUNT] = {0.97, 0.88, 0.70, 0.85, 0.92, 0.68, 0.80, 0.90};
     WsChoice best{WS_64x64, false, 1, 1e300};
     const int nkb = (g.K + WS_BK - 1) / WS_BK;
     for (int swap = 0; swap < 2; ++swap) {
@@ -229,7 +230,7 @@ void gemm(Ctx &ctx, GemmArgs g, bool a_kc, bool b_nc) {
     static const bool trace = getenv("QCP2_GEMM_TRACE") != nullptr;
     if (ws_eligible(ctx, g)) {
         WsChoice ch = ws_choose(ctx, g);
-        if (g.force_tile >= 0) ch.shape = g.force_tile & 7, ch.swap = (g.force_tile & 8) != 0, ch.split = 1;
+        if (g.force_tile >= 0) ch.shape = g.force_tile & 15, ch.swap = (g.force_tile & 16) != 0, ch.split = 1;
         if (g.force_split > 0) ch.split = g.force_split;
         if (trace)
             fprintf(stderr, "[qcp2 gemm] M %d N %d K %d batch %d  a_kc %d b_nc %d -> ws tile %dx%d%s split %d\n", g.M, g.N, g.K, g.batch,

@@ -14,7 +14,8 @@ const WsShapeInfo kWsShapes[WS_SHAPE_COUNT] = {{WsS80::BM, WsS80::BN, WsS80::STA
                                                {WsS64::BM, WsS64::BN, WsS64::STAGES},
                                                {WsS112::BM, WsS112::BN, WsS112::STAGES},
                                                {WsS16N::BM, WsS16N::BN, WsS16N::STAGES},
-                                               {WsS32::BM, WsS32::BN, WsS32::STAGES}};
+                                               {WsS32::BM, WsS32::BN, WsS32::STAGES},
+                                               {WsS96::BM, WsS96::BN, WsS96::STAGES}};
 
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,

@@ -426,13 +426,14 @@ void ws_launch_shape(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, c
 }
 
 // tile shapes (one translation unit each, dgemm_ws_*.cu)
-enum WsShapeId { WS_80x256 = 0, WS_48x256, WS_16x256, WS_64x64, WS_112x128, WS_16x192, WS_32x256, WS_SHAPE_COUNT };
+enum WsShapeId { WS_80x256 = 0, WS_48x256, WS_16x256, WS_64x64, WS_112x128, WS_16x192, WS_32x256, WS_96x128, WS_SHAPE_COUNT };
 using WsS80 = WsShape<2, 4, 5, 8>;  // the (T) tile: 40x64 per warp, 13 fragment loads per 40 DMMA
 using WsS48 = WsShape<1, 8, 6, 4>;  // M <= 48 (packed ladder, M = o(o-1)/2 = 45): 48x32 per warp
 using WsS16 = WsShape<1, 8, 2, 4>;  // M <= 16: HBM-bound streaming of the other operand
 using WsS64 = WsShape<2, 4, 4, 2>;  // small products / one-wave split-K
 using WsS112 = WsShape<2, 4, 7, 4>; // M = o^2 = 100
 using WsS32 = WsShape<1, 8, 4, 4>;  // 16 < M <= 32 (a spin class of i<j pairs: M = 25 at o = 10)
+using WsS96 = WsShape<2, 4, 6, 4>;  // 80 < M <= 96 (AO->MO at n = 86: 90 % of the rows are real, 77 % on the 112-row tile)
 using WsS16N = WsShape<1, 8, 2, 3>; // M <= 16, N = v = 162 and the like: 16x192 wastes less of the tensor pipe than 16x256
 struct WsShapeInfo {
     int bm, bn, stages;
@@ -445,5 +446,6 @@ void ws_launch_64x64(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, c
 void ws_launch_112x128(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
 void ws_launch_16x192(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
 void ws_launch_32x256(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
+void ws_launch_96x128(Ctx &ctx, const CUtensorMap &tmA, const CUtensorMap &tmB, const WsGemmArgs &g, bool a_kc, bool b_nc);
 
 }// namespace qcp2

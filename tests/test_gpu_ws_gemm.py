@@ -9,7 +9,7 @@ import qcp2_b200
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-TILES = {0: (80, 256), 1: (48, 256), 2: (16, 256), 3: (64, 64), 4: (112, 128), 5: (16, 192), 6: (32, 256)}
+TILES = {0: (80, 256), 1: (48, 256), 2: (16, 256), 3: (64, 64), 4: (112, 128), 5: (16, 192), 6: (32, 256), 7: (96, 128)}
 
 
 @pytest.fixture(scope="module")
@@ -68,7 +68,7 @@ def test_every_tile_and_layout_with_edges(dctx, tile, tA, tB):
 def test_transposed_problem(dctx, tile):
     bm, bn = TILES[tile]
     for tA, tB in [(0, 0), (1, 1), (0, 1)]:
-        _check(dctx, 2 * bn + 3, min(bm, 11), 50, tA, tB, tile + 8, seed=tile)
+        _check(dctx, 2 * bn + 3, min(bm, 11), 50, tA, tB, tile + 16, seed=tile)
 
 
 @pytest.mark.parametrize("tile,split", [(0, 3), (1, 8), (2, 5), (3, 37), (4, 11), (3, 293), (5, 148)])

@@ -39,8 +39,8 @@ def main():
              ("tau.<am||ef> packed 45x1620x13041 NT", 45, 1620, 13041, 0, 1, [(-1, 0), (1, 8), (1, 16), (1, 21)]),
              ("tau.<am||ef> dense 100x1620x26244 NT", 100, 1620, 26244, 0, 1, [(-1, 0), (4, 11)]),
              ("skinny 10x262440x162 NT", 10, 262440, 162, 0, 1, [(-1, 0), (2, 1)]),
-             ("skinny 262440x10x162 NN", 262440, 10, 162, 0, 0, [(-1, 0), (10, 1)]),
-             ("AO->MO 86x636056x86 TT", 86, 636056, 86, 1, 1, [(-1, 0), (4, 1), (0, 1)])]
+             ("skinny 262440x10x162 NN", 262440, 10, 162, 0, 0, [(-1, 0), (18, 1)]),
+             ("AO->MO 86x636056x86 TT", 86, 636056, 86, 1, 1, [(-1, 0), (4, 1), (0, 1), (7, 1)])]
     for name, M, N, K, tA, tB, variants in cases:
         sa = (K, M) if tA else (M, K)
         sb = (N, K) if tB else (K, N)

@@ -162,7 +162,12 @@ int qcp2_comm_allgather(qcp2_ctx *ctx, const double *dev_send, double *dev_recv,
  * doubles) may be NULL.  The ROOT's `mode` decides for everyone (it travels in the broadcast header), and a
  * failure on any rank before the payload broadcasts makes every rank return status 1 together.
  * Host buffers should be pinned (cudaHostAlloc / cudaHostRegister): pageable memory is staged synchronously by
- * the driver, which serialises the <vo||vv> upload with the compute it is meant to overlap. */
+ * the driver, which serialises the <vo||vv> upload with the compute it is meant to overlap.
+ * Replicated host inputs: the other ranks MAY pass the seven tensors as well (host pointers; they must hold the root's values --
+ * typically every rank maps one shared-memory copy).  When every rank does, each uploads the small tensors itself and the
+ * <vo||vv> slabs are dealt over the ranks (slab i is uploaded and packed by rank i mod W over its own PCIe link and broadcast
+ * from there), so the host-to-device traffic is spread over W links instead of the root's one.  Same energy, bit for bit.
+ * QCP2_T_ROOT_UPLOAD=1 keeps the root-only upload. */
 int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
                      const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode, int root,
                      double *e_triples, double *energy);

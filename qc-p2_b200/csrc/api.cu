@@ -687,10 +687,24 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
         DBuf hdr(c, 4);
         double hh[4] = {0.0, 0.0, 0.0, 0.0};
         std::string local_err;
+        // Replicated host inputs: a rank other than the root may pass the tensors as well (HOST mode; they must hold the root's
+        // values, e.g. mappings of one shared-memory copy).  When EVERY rank does, each uploads the small tensors itself and the
+        // <vo||vv> slabs are dealt over the ranks (slab i by rank i % W over its own PCIe link), instead of everything
+        // crossing the root's link and NVLink.
+        const bool have_all = T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v && c.pointer_mode == QCP2_HOST &&
+                              !getenv("QCP2_T_ROOT_UPLOAD");
+        double vote = have_all ? 1.0 : 0.0;
         try {
             if (is_root) QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v, "(T) mgpu: the root rank must supply every tensor");
-            for (int k = 0; k < 7; ++k)
-                if (k != kW) place(k);
+            for (int k = 0; k < 7; ++k) {
+                if (k == kW) continue;
+                if (!is_root && have_all) {// optimistic own upload; used only if every rank has the tensors
+                    staged[k] = In(c, src[k], sizes[k]);
+                    dev[k] = const_cast<double *>(staged[k].p);
+                } else {
+                    place(k);
+                }
+            }
             if (is_root) {
                 int m = mode;
                 bool streamed = false;
@@ -709,11 +723,13 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
             local_err = e.what();
             cudaGetLastError();
         }
-        comm_agree(c, cm, local_err, "(T) mgpu");
+        comm_agree(c, cm, local_err, "(T) mgpu", &vote);
+        const bool replicated = cm.nranks > 1 && vote == (double) cm.nranks;
         if (is_root) QCP2_CUDA(cudaMemcpyAsync(hdr.p, hh, 32, cudaMemcpyHostToDevice, c.stream));
         comm_broadcast(c, cm, hdr.p, 4, root);
-        for (int k = 0; k < 7; ++k)
-            if (k != kW) comm_broadcast(c, cm, dev[k], sizes[k], root);
+        if (!replicated)
+            for (int k = 0; k < 7; ++k)
+                if (k != kW) comm_broadcast(c, cm, dev[k], sizes[k], root);
         QCP2_CUDA(cudaMemcpyAsync(hh, hdr.p, 32, cudaMemcpyDeviceToHost, c.stream));
         c.sync();
         tr.mark("stage + broadcast the small inputs");
@@ -725,7 +741,7 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
         bool done = false;
         if (streamed) {
             TStream ts;
-            ts.vovv_host = is_root ? vovv : nullptr, ts.comm = &cm, ts.root = root;
+            ts.vovv_host = (is_root || replicated) ? vovv : nullptr, ts.comm = &cm, ts.root = root, ts.dealt = replicated;
             t_evaluate(c, E, dev[kT1], dev[kT2], dev[kG], nullptr, dev[kX], dev[kEo], dev[kEv], o, v, QCP2_T_SYMMETRIC, &ts, cm.rank,
                        cm.nranks, -1, true, tr);
             done = true;

@@ -113,24 +113,26 @@ void comm_allreduce_sum(Ctx &ctx, Comm &comm, double *buf, long long n) {
 // Collective error agreement: every rank contributes 0 (fine) or 1 (local_err is not empty); the sum is read
 // back and, if any rank failed, EVERY rank throws -- so a failure on one rank before a payload collective
 // can no longer leave the others blocked in it (qcp2_ccsd_t_mgpu / qcp2_post_hf_mgpu hang).
-void comm_agree(Ctx &ctx, Comm &comm, const std::string &local_err, const char *where) {
+void comm_agree(Ctx &ctx, Comm &comm, const std::string &local_err, const char *where, double *vote) {
     if (comm.nranks == 1) {
         if (!local_err.empty()) throw Error(local_err);
         return;
     }
-    double *flag = ctx.alloc(1);
-    const double mine = local_err.empty() ? 0.0 : 1.0;
-    double total = 0.0;
+    double *flag = ctx.alloc(2);
+    const double mine[2] = {local_err.empty() ? 0.0 : 1.0, vote ? *vote : 0.0};
+    double sums[2] = {0.0, 0.0};
     try {
-        QCP2_CUDA(cudaMemcpyAsync(flag, &mine, 8, cudaMemcpyHostToDevice, ctx.stream));
-        comm_allreduce_sum(ctx, comm, flag, 1);
-        QCP2_CUDA(cudaMemcpyAsync(&total, flag, 8, cudaMemcpyDeviceToHost, ctx.stream));
+        QCP2_CUDA(cudaMemcpyAsync(flag, mine, 16, cudaMemcpyHostToDevice, ctx.stream));
+        comm_allreduce_sum(ctx, comm, flag, 2);
+        QCP2_CUDA(cudaMemcpyAsync(sums, flag, 16, cudaMemcpyDeviceToHost, ctx.stream));
         ctx.sync();
     } catch (...) {
         ctx.free(flag);
         throw;
     }
     ctx.free(flag);
+    const double total = sums[0];
+    if (vote) *vote = sums[1];
     if (total != 0.0) {
         if (!local_err.empty()) throw Error(local_err);
         throw Error(std::string(where) + ": " + std::to_string((int) total) + " other rank(s) failed before the exchange; nothing was computed");

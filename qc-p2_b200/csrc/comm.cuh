@@ -19,7 +19,8 @@ void comm_broadcast(Ctx &ctx, Comm &comm, double *buf, long long n, int root);
 void comm_broadcast_bytes(Ctx &ctx, Comm &comm, void *buf, long long nbytes, int root);
 void comm_allreduce_sum(Ctx &ctx, Comm &comm, double *buf, long long n);
 // all ranks throw if any rank's local_err is non-empty (one 8-byte all-reduce); see comm.cu
-void comm_agree(Ctx &ctx, Comm &comm, const std::string &local_err, const char *where);
+// `vote` (optional): every rank's value is summed in the same exchange and the sum returned in place
+void comm_agree(Ctx &ctx, Comm &comm, const std::string &local_err, const char *where, double *vote = nullptr);
 // several collectives issued as one NCCL group (e.g. one broadcast per rank with unequal counts)
 void comm_group_start();
 void comm_group_end();

@@ -502,8 +502,11 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
         if (sym) pack(oovv, O, O, 0, P->oovvP);
         if (ts) {
             const bool multi = ts->comm && ts->comm->nranks > 1;
-            const bool is_root = !multi || ts->comm->rank == ts->root;
-            if (is_root) QCP2_REQUIRE(ts->vovv_host != nullptr, "(T): the root rank must supply the host <vo||vv>");
+            const bool dealt = multi && ts->dealt;
+            const int W = multi ? ts->comm->nranks : 1, me = multi ? ts->comm->rank : 0;
+            auto owner = [&](long long i) { return dealt ? (int) (i % W) : ts->root; };// the rank that uploads and packs slab i
+            const bool is_root = !multi || dealt || me == ts->root;                  // "this rank uploads slabs"
+            if (is_root) QCP2_REQUIRE(ts->vovv_host != nullptr, "(T): a rank that uploads slabs must supply the host <vo||vv>");
             {// highest priority: the short pack / broadcast kernels must not queue behind the GEMM's CTAs
                 int least = 0, greatest = 0;
                 QCP2_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
@@ -512,6 +515,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
             QCP2_CUDA(cudaMalloc(&P->vovv_defect, 16));
             QCP2_CUDA(cudaMemsetAsync(P->vovv_defect, 0, 16, ctx.stream));
             if (is_root) P->stage = DBuf(ctx, (size_t) (V * V * V));
+            if (dealt) P->defect_all = DBuf(ctx, (size_t) (2 * W)), P->defect_ranks = W;
             // the copy stream starts once the stream-ordered allocations above exist
             cudaEvent_t born;
             QCP2_CUDA(cudaEventCreateWithFlags(&born, cudaEventDisableTiming));
@@ -520,7 +524,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
             cudaStream_t main_stream = ctx.stream;
             for (long long i = 0; i < O; ++i) {
                 double *slabP = P->vovvP.p + i * V * np;
-                if (is_root) {
+                if (is_root && (!multi || owner(i) == me)) {
                     // vovv[e][i][b][c]: v rows of v^2 doubles, o*v^2 apart -> stage[e][b][c]
                     QCP2_CUDA(cudaMemcpy2DAsync(P->stage.p, (size_t) (V * V) * 8, ts->vovv_host + i * V * V, (size_t) (O * V * V) * 8,
                                                 (size_t) (V * V) * 8, (size_t) V, cudaMemcpyHostToDevice, P->copy));
@@ -531,7 +535,7 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
                 if (multi) {
                     ctx.stream = P->copy;// enqueue the collective on the copy stream
                     try {
-                        comm_broadcast(ctx, *ts->comm, slabP, V * np, ts->root);
+                        comm_broadcast(ctx, *ts->comm, slabP, V * np, owner(i));
                     } catch (...) {
                         ctx.stream = main_stream;
                         throw;
@@ -543,10 +547,14 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
                 QCP2_CUDA(cudaEventRecord(ready, P->copy));
                 P->slab_ready.push_back(ready);
             }
-            if (multi) {// every rank learns the root's verdict on the (b,c) antisymmetry
+            if (multi) {// every rank learns the verdict on the (b,c) antisymmetry: the root's, or (dealt) every packer's
                 ctx.stream = P->copy;
                 try {
-                    comm_broadcast_bytes(ctx, *ts->comm, P->vovv_defect, 16, ts->root);
+                    if (dealt) {
+                        comm_allgather(ctx, *ts->comm, reinterpret_cast<const double *>(P->vovv_defect), P->defect_all.p, 2);
+                    } else {
+                        comm_broadcast_bytes(ctx, *ts->comm, P->vovv_defect, 16, ts->root);
+                    }
                 } catch (...) {
                     ctx.stream = main_stream;
                     throw;
@@ -607,6 +615,13 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
 void t_plan_vovv_defect(TPlan &P, double *defect, double *maxabs) {
     QCP2_REQUIRE(P.copy && P.vovv_defect, "(T): not a streamed plan");
     QCP2_CUDA(cudaStreamSynchronize(P.copy));
+    if (P.defect_ranks > 0) {// dealt upload: the worst record over the packing ranks
+        std::vector<double> h((size_t) (2 * P.defect_ranks));
+        QCP2_CUDA(cudaMemcpy(h.data(), P.defect_all.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        *defect = 0.0, *maxabs = 0.0;
+        for (int r = 0; r < P.defect_ranks; ++r) *defect = std::max(*defect, h[(size_t) (2 * r)]), *maxabs = std::max(*maxabs, h[(size_t) (2 * r + 1)]);
+        return;
+    }
     unsigned long long h[2];
     QCP2_CUDA(cudaMemcpy(h, P.vovv_defect, 16, cudaMemcpyDeviceToHost));
     long long b0 = (long long) h[0], b1 = (long long) h[1];

@@ -59,7 +59,9 @@ struct TPlan {
     cudaStream_t copy = nullptr;
     std::vector<cudaEvent_t> slab_ready;  // one per occupied index
     DBuf stage;
-    unsigned long long *vovv_defect = nullptr;// device [2]: max |x[e,b,c] + x[e,c,b]|, max |x| over the slabs
+    unsigned long long *vovv_defect = nullptr;// device [2]: max |x[e,b,c] + x[e,c,b]|, max |x| over the slabs this rank packed
+    DBuf defect_all;                // dealt upload: the [2]-records of every rank (all-gathered)
+    int defect_ranks = 0;
     bool merged_o = false;          // the three hole segments share one padded K block (TMA kernel only)
     bool use_tma = false;           // the TMA/mbarrier kernel (t_gemm_tma.cu) runs the triples GEMM (both modes)
     long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
@@ -73,6 +75,9 @@ struct TStream {
     const double *vovv_host = nullptr;
     Comm *comm = nullptr;
     int root = 0;
+    // every rank holds the same host tensor (e.g. one shared-memory copy): slab i is uploaded and packed by rank i % W over its
+    // own PCIe link and broadcast from there, so the 20 GB of H2D traffic are spread over W links instead of the root's one
+    bool dealt = false;
 };
 // vovv is a device pointer, or null together with a TStream (SYMMETRIC mode only)
 TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,

@@ -36,6 +36,12 @@ for (o, v) in ((7, 30), (6, 33)):              # v(v-1)/2 even and odd
     box = [None] * world
     dist.all_gather_object(box, (e, single))
     out["t_o%dv%d" % (o, v)] = {"mgpu": e, "single": single, "all_ranks": box}
+# replicated host inputs: EVERY rank passes the (identical) tensors -> the <vo||vv> slabs are dealt over the ranks' PCIe links
+s = npo.synthetic_t_inputs(7, 30)
+e_rep = ctx.CCSD_T_mgpu(*[s[k] for k in names], 7, 30, qcp2_b200.T_AUTO, root=0)
+box = [None] * world
+dist.all_gather_object(box, e_rep)
+out["t_replicated_host"] = {"mgpu": e_rep, "single": out["t_o7v30"]["single"], "all_ranks": box}
 case = rhf_case(8, 3, 5)                        # seeded RHF-type pseudo-molecule, n = 8 spatial orbitals
 args = (case["ao"], case["C"], None, case["eps"], None) if rank == 0 else (None,) * 5
 m = ctx.post_hf_mgpu(*args, case["ao"].shape[0], case["no"], case["nv"], maxiter=60, cc_conv=1e-12)
@@ -76,6 +82,11 @@ def test_two_rank_triples_energy_is_bit_identical(two_rank_result):
         rec = two_rank_result[key]
         assert rec["mgpu"] == rec["single"], rec                       # bit for bit
         assert all(tuple(b) == (rec["mgpu"], rec["single"]) for b in rec["all_ranks"]), rec
+
+
+def test_two_rank_dealt_upload_is_bit_identical(two_rank_result):
+    rec = two_rank_result["t_replicated_host"]
+    assert rec["mgpu"] == rec["single"] and all(b == rec["mgpu"] for b in rec["all_ranks"]), rec
 
 
 def test_two_rank_post_hf_matches_one_rank(two_rank_result):

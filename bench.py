@@ -664,14 +664,15 @@ def main():
         ref_e, ref_s, ref_o, ref_v, ref_file = committed_n1_e2e()
         comparable = ref_e is not None and (ref_o, ref_v) == (o, v)
         if shared is not None:
-            h2d = sum(d_numel[k] for k in names if k != "vovv") * 8 * world + d_numel["vovv"] * 8  # small tensors per rank + <vo||vv> once
+            # every large tensor crosses PCIe once in total (1/W of it per rank); T1 and the orbital energies on every rank
+            h2d = sum(d_numel.values()) * 8 + (world - 1) * (d_numel["T1"] + d_numel["eps_o"] + d_numel["eps_v"]) * 8
             shared.close()
         e2e = {"value": nt * fpt / float(dt[0]) / 1e12, "unit": UNIT,
                # E(T) of the whole job against the committed one-GPU value, bit for bit (fixed triple->slot map + fixed-order sum)
                "e_t_matches_n1": (e_job == ref_e) if comparable else None, "e_t_n1": ref_e if comparable else None,
                # whole-job strong scaling: T(1 GPU, committed record) / (N x T(N GPUs, this run)); at N=1 it compares boxes
                "strong_scaling_efficiency": ref_s / (world * float(dt[0])) if comparable else None,
-               "n1_record": ref_file if comparable else None, "h2d_bytes_per_step": h2d if rank == 0 else 0,
+               "n1_record": ref_file if comparable else None, "h2d_bytes_per_step": h2d,
                "host_buffers": ("one POSIX shared-memory copy mapped and pinned (cudaHostRegister) by every rank; <vo||vv> slabs dealt over the "
                                 "ranks' PCIe links" if shared is not None else "pinned on rank 0" if world > 1 else "pinned"),
                "d2h_bytes_per_step": 8 * (nt + 1), "steps": 1, "seconds": float(dt[0]), "e_t": e_job,

@@ -694,18 +694,48 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
         const bool have_all = T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v && c.pointer_mode == QCP2_HOST &&
                               !getenv("QCP2_T_ROOT_UPLOAD");
         double vote = have_all ? 1.0 : 0.0;
+        if (is_root && !(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v)) local_err = "(T) mgpu: the root rank must supply every tensor";
+        comm_agree(c, cm, local_err, "(T) mgpu", &vote);
+        const bool replicated = cm.nranks > 1 && vote == (double) cm.nranks;
         try {
-            if (is_root) QCP2_REQUIRE(T1 && T2 && oovv && vovv && ovoo && eps_o && eps_v, "(T) mgpu: the root rank must supply every tensor");
-            for (int k = 0; k < 7; ++k) {
-                if (k == kW) continue;
-                if (!is_root && have_all) {// optimistic own upload; used only if every rank has the tensors
-                    staged[k] = In(c, src[k], sizes[k]);
-                    dev[k] = const_cast<double *>(staged[k].p);
-                } else {
-                    place(k);
+            if (replicated) {
+                // every rank holds the host tensors: rank r uploads the r-th of W equal chunks of T2, <oo||vv> and <ov||oo> over its
+                // own PCIe link and ONE in-place ncclAllGather per tensor assembles them everywhere (NVLink); T1 and the orbital
+                // energies (kilobytes) are uploaded by every rank
+                const int W = cm.nranks;
+                for (int k = 0; k < 7; ++k) {
+                    if (k == kW) continue;
+                    if (k == kT1 || k == kEo || k == kEv) {
+                        staged[k] = In(c, src[k], sizes[k]);
+                        dev[k] = const_cast<double *>(staged[k].p);
+                        continue;
+                    }
+                    const long long per = (sizes[k] + W - 1) / W, lo = std::min(sizes[k], per * cm.rank), hi = std::min(sizes[k], lo + per);
+                    scratch[k] = DBuf(c, (size_t) std::max<long long>(per * W, 1));
+                    dev[k] = scratch[k].p;
+                    if (hi > lo)
+                        QCP2_CUDA(cudaMemcpyAsync(dev[k] + lo, src[k] + lo, (size_t) (hi - lo) * 8, cudaMemcpyHostToDevice, c.stream));
                 }
+            } else {
+                for (int k = 0; k < 7; ++k)
+                    if (k != kW) place(k);
             }
+            c.sync();
+        } catch (const std::exception &e) {
+            local_err = e.what();
+            cudaGetLastError();
+        }
+        comm_agree(c, cm, local_err, "(T) mgpu, staging");
+        if (replicated) {
+            const int W = cm.nranks;
+            for (int k : {(int) kT2, (int) kG, (int) kX}) {
+                const long long per = (sizes[k] + W - 1) / W;
+                comm_allgather(c, cm, dev[k] + per * cm.rank, dev[k], per);
+            }
+        }
+        try {
             if (is_root) {
+                if (!replicated) c.sync();
                 int m = mode;
                 bool streamed = false;
                 if (stream_allowed(c, mode, o, v) &&
@@ -723,8 +753,7 @@ int qcp2_ccsd_t_mgpu(qcp2_ctx *ctx, const double *T1, const double *T2, const do
             local_err = e.what();
             cudaGetLastError();
         }
-        comm_agree(c, cm, local_err, "(T) mgpu", &vote);
-        const bool replicated = cm.nranks > 1 && vote == (double) cm.nranks;
+        comm_agree(c, cm, local_err, "(T) mgpu, mode selection");
         if (is_root) QCP2_CUDA(cudaMemcpyAsync(hdr.p, hh, 32, cudaMemcpyHostToDevice, c.stream));
         comm_broadcast(c, cm, hdr.p, 4, root);
         if (!replicated)

@@ -95,14 +95,14 @@ void comm_destroy(Comm *comm) {
     delete comm;
 }
 
-void comm_broadcast(Ctx &ctx, Comm &comm, double *buf, long long n, int root) {
+void comm_broadcast(Ctx &ctx, Comm &comm, double *buf, long long n, int root, cudaStream_t stream) {
     if (n <= 0 || comm.nranks == 1) return;
-    check(api().Broadcast(buf, buf, (size_t) n, kNcclFloat64, root, comm.nccl, ctx.stream), "ncclBroadcast");
+    check(api().Broadcast(buf, buf, (size_t) n, kNcclFloat64, root, comm.nccl, stream ? stream : ctx.stream), "ncclBroadcast");
 }
 
-void comm_broadcast_bytes(Ctx &ctx, Comm &comm, void *buf, long long nbytes, int root) {
+void comm_broadcast_bytes(Ctx &ctx, Comm &comm, void *buf, long long nbytes, int root, cudaStream_t stream) {
     if (nbytes <= 0 || comm.nranks == 1) return;
-    check(api().Broadcast(buf, buf, (size_t) nbytes, kNcclUint8, root, comm.nccl, ctx.stream), "ncclBroadcast");
+    check(api().Broadcast(buf, buf, (size_t) nbytes, kNcclUint8, root, comm.nccl, stream ? stream : ctx.stream), "ncclBroadcast");
 }
 
 void comm_allreduce_sum(Ctx &ctx, Comm &comm, double *buf, long long n) {
@@ -142,13 +142,14 @@ void comm_agree(Ctx &ctx, Comm &comm, const std::string &local_err, const char *
 void comm_group_start() { check(api().GroupStart(), "ncclGroupStart"); }
 void comm_group_end() { check(api().GroupEnd(), "ncclGroupEnd"); }
 
-void comm_allgather(Ctx &ctx, Comm &comm, const double *send, double *recv, long long n_per_rank) {
+void comm_allgather(Ctx &ctx, Comm &comm, const double *send, double *recv, long long n_per_rank, cudaStream_t stream) {
     if (n_per_rank <= 0) return;
+    cudaStream_t st = stream ? stream : ctx.stream;
     if (comm.nranks == 1) {
-        if (send != recv) QCP2_CUDA(cudaMemcpyAsync(recv, send, (size_t) n_per_rank * 8, cudaMemcpyDeviceToDevice, ctx.stream));
+        if (send != recv) QCP2_CUDA(cudaMemcpyAsync(recv, send, (size_t) n_per_rank * 8, cudaMemcpyDeviceToDevice, st));
         return;
     }
-    check(api().AllGather(send, recv, (size_t) n_per_rank, kNcclFloat64, comm.nccl, ctx.stream), "ncclAllGather");
+    check(api().AllGather(send, recv, (size_t) n_per_rank, kNcclFloat64, comm.nccl, st), "ncclAllGather");
 }
 
 }// namespace qcp2

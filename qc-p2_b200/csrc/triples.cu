@@ -428,6 +428,7 @@ int t_select_mode(Ctx &ctx, const double *T2, const double *oovv, const double *
 }
 
 TPlan::~TPlan() {
+    if (slab_thread.joinable()) slab_thread.join();
     if (ctx) {
         if (copy) cudaStreamSynchronize(copy);
         cudaStreamSynchronize(ctx->stream);
@@ -447,6 +448,60 @@ TPlan::~TPlan() {
     if (ijk_dev) cudaFree(ijk_dev);
     if (items_dev) cudaFree(items_dev);
     if (aux) cudaStreamDestroy(aux);
+}
+
+// streamed <vo||vv>, body of the helper thread: every slab in index order on the copy stream -- upload + pack on the owning rank,
+// broadcast with a communicator, event; after the last slab the antisymmetry verdict is exchanged.  Same order on every rank.
+static void slab_thread_main(TPlan *Pp) {
+    TPlan &P = *Pp;
+    Ctx &ctx = *P.ctx;
+    const long long O = P.o, V = P.v, np = P.ld;
+    const TStream &ts = P.src;
+    const bool multi = P.src_multi, dealt = multi && ts.dealt;
+    const int W = multi ? ts.comm->nranks : 1, me = multi ? ts.comm->rank : 0;
+    auto owner = [&](long long i) { return dealt ? (int) (i % W) : ts.root; };
+    try {
+        QCP2_CUDA(cudaSetDevice(ctx.device));
+        for (long long i = 0; i < O; ++i) {
+            double *slabP = P.vovvP.p + i * V * np;
+            if (P.src_uploads && (!multi || owner(i) == me)) {
+                // vovv[e][i][b][c]: v rows of v^2 doubles, o*v^2 apart -> stage[e][b][c]
+                QCP2_CUDA(cudaMemcpy2DAsync(P.stage.p, (size_t) (V * V) * 8, ts.vovv_host + i * V * V, (size_t) (O * V * V) * 8,
+                                            (size_t) (V * V) * 8, (size_t) V, cudaMemcpyHostToDevice, P.copy));
+                pack_slab_kernel<<<grid_for(V * V * V, kBlock, ctx.sm_count, 4), kBlock, 0, P.copy>>>(P.stage.p, P.v, slabP, np, P.vovv_defect);
+                QCP2_CUDA(cudaGetLastError());
+                ++P.slab_launches;
+            }
+            if (multi) comm_broadcast(ctx, *ts.comm, slabP, V * np, owner(i), P.copy);
+            QCP2_CUDA(cudaEventRecord(P.slab_ready[(size_t) i], P.copy));
+            if (i == O - 1 && multi) {// every rank learns the verdict on the (b,c) antisymmetry: the root's, or (dealt) every packer's
+                if (dealt) comm_allgather(ctx, *ts.comm, reinterpret_cast<const double *>(P.vovv_defect), P.defect_all.p, 2, P.copy);
+                else comm_broadcast_bytes(ctx, *ts.comm, P.vovv_defect, 16, ts.root, P.copy);
+            }
+            {
+                std::lock_guard<std::mutex> lk(P.slab_mutex);
+                P.slabs_enqueued = i + 1;
+            }
+            P.slab_cv.notify_all();
+        }
+    } catch (const std::exception &e) {
+        {
+            std::lock_guard<std::mutex> lk(P.slab_mutex);
+            P.slab_error = e.what();
+        }
+        P.slab_cv.notify_all();
+    }
+}
+void t_plan_wait_slab(TPlan &P, long long i) {
+    std::unique_lock<std::mutex> lk(P.slab_mutex);
+    P.slab_cv.wait(lk, [&] { return P.slabs_enqueued > i || !P.slab_error.empty(); });
+    if (!P.slab_error.empty()) throw Error("(T) slab pipeline: " + P.slab_error);
+}
+void t_plan_join_slabs(TPlan &P) {
+    if (P.slab_thread.joinable()) P.slab_thread.join();
+    P.ctx->launches += P.slab_launches;
+    P.slab_launches = 0;
+    if (!P.slab_error.empty()) throw Error("(T) slab pipeline: " + P.slab_error);
 }
 
 TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
@@ -521,46 +576,17 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
             QCP2_CUDA(cudaEventCreateWithFlags(&born, cudaEventDisableTiming));
             QCP2_CUDA(cudaEventRecord(born, ctx.stream));
             QCP2_CUDA(cudaStreamWaitEvent(P->copy, born, 0));
-            cudaStream_t main_stream = ctx.stream;
+            // The slab pipeline is enqueued by a helper thread (see TPlan): a long queue of NCCL broadcasts behind the first uploads
+            // makes the host block in ncclBroadcast until the uploads drain (8 ranks: 0.37 s), which must not keep the main thread
+            // from launching the triples whose slabs have arrived.
+            P->src = *ts, P->src_multi = multi, P->src_uploads = is_root;
             for (long long i = 0; i < O; ++i) {
-                double *slabP = P->vovvP.p + i * V * np;
-                if (is_root && (!multi || owner(i) == me)) {
-                    // vovv[e][i][b][c]: v rows of v^2 doubles, o*v^2 apart -> stage[e][b][c]
-                    QCP2_CUDA(cudaMemcpy2DAsync(P->stage.p, (size_t) (V * V) * 8, ts->vovv_host + i * V * V, (size_t) (O * V * V) * 8,
-                                                (size_t) (V * V) * 8, (size_t) V, cudaMemcpyHostToDevice, P->copy));
-                    pack_slab_kernel<<<grid_for(V * V * V, kBlock, ctx.sm_count, 4), kBlock, 0, P->copy>>>(P->stage.p, v, slabP, np,
-                                                                                                         P->vovv_defect);
-                    ctx.launched("pack_slab");
-                }
-                if (multi) {
-                    ctx.stream = P->copy;// enqueue the collective on the copy stream
-                    try {
-                        comm_broadcast(ctx, *ts->comm, slabP, V * np, owner(i));
-                    } catch (...) {
-                        ctx.stream = main_stream;
-                        throw;
-                    }
-                    ctx.stream = main_stream;
-                }
                 cudaEvent_t ready;
                 QCP2_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-                QCP2_CUDA(cudaEventRecord(ready, P->copy));
                 P->slab_ready.push_back(ready);
             }
-            if (multi) {// every rank learns the verdict on the (b,c) antisymmetry: the root's, or (dealt) every packer's
-                ctx.stream = P->copy;
-                try {
-                    if (dealt) {
-                        comm_allgather(ctx, *ts->comm, reinterpret_cast<const double *>(P->vovv_defect), P->defect_all.p, 2);
-                    } else {
-                        comm_broadcast_bytes(ctx, *ts->comm, P->vovv_defect, 16, ts->root);
-                    }
-                } catch (...) {
-                    ctx.stream = main_stream;
-                    throw;
-                }
-                ctx.stream = main_stream;
-            }
+            QCP2_CUDA(cudaStreamSynchronize(ctx.stream));// the packed buffers and `stage` exist before the helper thread touches them
+            P->slab_thread = std::thread(slab_thread_main, P.get());
             cudaEventDestroy(born);
         }
     }
@@ -665,7 +691,10 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
     P.last_gemm_seconds = P.last_total_seconds = 0.0;
     P.last_gemm_launches = 0;
     const long long launches0 = ctx.launches;
-    if (count == 0 || P.ncols == 0) return;
+    if (count == 0 || P.ncols == 0) {
+        if (!P.slab_ready.empty()) t_plan_join_slabs(P);// a rank without triples still takes part in every slab exchange
+        return;
+    }
     const bool sym = P.mode == QCP2_T_SYMMETRIC;
     const long long O = P.o, V = P.v, nc = P.ld;// row stride of the packed tensors and of X (the pad column is computed along)
 
@@ -734,6 +763,7 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         if (streamed) {// the batch's B rows: slabs up to its largest occupied index (the copy stream is in order)
             int kmax = 0;
             for (int q = 0; q < cnt; ++q) kmax = std::max(kmax, ijk[(size_t) (3 * (off + q) + 2)]);
+            t_plan_wait_slab(P, kmax);// host side: the event below must have been recorded (enqueued) by the slab thread
             QCP2_CUDA(cudaStreamWaitEvent(ctx.stream, P.slab_ready[(size_t) kmax], 0));
         }
         BuildAArgs ba;
@@ -806,6 +836,7 @@ void t_plan_run(TPlan &P, long long first, long long stride, long long max_count
         ctx.launched("t_finish");
         QCP2_CUDA(cudaEventRecord(P.energy_done[s], P.aux));
     }
+    if (streamed) t_plan_join_slabs(P);// every slab has been enqueued; the communicator is the main thread's again
     for (int s = 0; s < 2 && s < nbatch; ++s) QCP2_CUDA(cudaStreamWaitEvent(ctx.stream, P.energy_done[s], 0));
     QCP2_CUDA(cudaEventRecord(P.t_end, ctx.stream));
     std::vector<double> e_host((size_t) count);

@@ -2,6 +2,10 @@
 // time: one segmented-K DMMA GEMM X = A.B (M = v, K = 3(v+o)) per triple plus a fused
 // permute-combine / denominator / energy sweep.  No o^3 v^3 tensor is ever materialised.
 #pragma once
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -25,6 +29,18 @@ struct TmaGemmArgs {
     int merged_sub_rows = 0;     // > 0: segment 3 is the merged hole block, rows [q s, (q+1) s) come from seg->B[3 + q]
 };
 void launch_t_gemm_tma(Ctx &ctx, const TmaGemmArgs &g, int batch);
+
+struct Comm;
+// where a streamed plan gets <vo||vv> from: the root rank's HOST tensor [v][o][v][v] (null on the
+// other ranks), broadcast slab by slab when a communicator with more than one rank is given
+struct TStream {
+    const double *vovv_host = nullptr;
+    Comm *comm = nullptr;
+    int root = 0;
+    // every rank holds the same host tensor (e.g. one shared-memory copy): slab i is uploaded and packed by rank i % W over its
+    // own PCIe link and broadcast from there, so the 20 GB of H2D traffic are spread over W links instead of the root's one
+    bool dealt = false;
+};
 
 struct TPlan {
     Ctx *ctx = nullptr;
@@ -62,23 +78,26 @@ struct TPlan {
     unsigned long long *vovv_defect = nullptr;// device [2]: max |x[e,b,c] + x[e,c,b]|, max |x| over the slabs this rank packed
     DBuf defect_all;                // dealt upload: the [2]-records of every rank (all-gathered)
     int defect_ranks = 0;
+    // Streamed plans: the slab pipeline (upload + pack on the owning rank, ncclBroadcast, event) is enqueued by a helper
+    // thread.  With a queue of NCCL calls behind the first uploads the host blocks inside ncclBroadcast until the uploads
+    // drain (8 ranks: 0.37 s); on a helper thread that wait no longer keeps the main thread from launching the triples whose
+    // slabs have arrived.  The main thread waits (host side) until the slab it needs has been ENQUEUED -- a
+    // cudaStreamWaitEvent on a not yet recorded event would be a no-op -- and joins the thread before it touches the
+    // communicator again.
+    TStream src;
+    bool src_multi = false, src_uploads = false;
+    std::thread slab_thread;
+    std::mutex slab_mutex;
+    std::condition_variable slab_cv;
+    long long slabs_enqueued = 0;   // guarded by slab_mutex
+    std::string slab_error;         // guarded by slab_mutex
+    long long slab_launches = 0;
     bool merged_o = false;          // the three hole segments share one padded K block (TMA kernel only)
     bool use_tma = false;           // the TMA/mbarrier kernel (t_gemm_tma.cu) runs the triples GEMM (both modes)
     long long a_per_triple = 0;     // doubles of A per triple (tiled or plain layout)
     ~TPlan();
 };
 
-struct Comm;
-// where a streamed plan gets <vo||vv> from: the root rank's HOST tensor [v][o][v][v] (null on the
-// other ranks), broadcast slab by slab when a communicator with more than one rank is given
-struct TStream {
-    const double *vovv_host = nullptr;
-    Comm *comm = nullptr;
-    int root = 0;
-    // every rank holds the same host tensor (e.g. one shared-memory copy): slab i is uploaded and packed by rank i % W over its
-    // own PCIe link and broadcast from there, so the 20 GB of H2D traffic are spread over W links instead of the root's one
-    bool dealt = false;
-};
 // vovv is a device pointer, or null together with a TStream (SYMMETRIC mode only)
 TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double *oovv, const double *vovv,
                      const double *ovoo, const double *eps_o, const double *eps_v, int o, int v, int mode,
@@ -86,6 +105,8 @@ TPlan *t_plan_create(Ctx &ctx, const double *T1, const double *T2, const double 
 // streamed plans: waits for the last slab and returns the antisymmetry defect of vovv in (b,c) seen by
 // the rank that packed it (after a broadcast: by every rank)
 void t_plan_vovv_defect(TPlan &plan, double *defect, double *maxabs);
+void t_plan_wait_slab(TPlan &plan, long long i);   // host wait until slab i has been enqueued (throws the thread's error)
+void t_plan_join_slabs(TPlan &plan);               // all slabs enqueued, helper thread gone
 // evaluates triples first, first+stride, ... (< ntriples, at most max_count of them);
 // e_triples_dev (device, ntriples doubles, may be null) receives each triple's weighted
 // contribution at its global index; returns the partial sum in *energy_host.

@@ -539,6 +539,14 @@ def main():
         # the library's own NCCL communicator (qcp2_comm_*); torch.distributed only carries the
         # 128-byte bootstrap id, the barriers and the max-over-ranks of the timings
         ctx.comm_init_from_torch(dist)
+        # communicator warm-up (NCCL builds its channels lazily, per collective, on first use): one tiny broadcast from every
+        # root, one all-gather, one all-reduce -- so that no connection set-up lands inside a timed region
+        wbuf = torch.zeros(8 * world, dtype=torch.float64, device="cuda")
+        for r in range(world):
+            ctx.comm_broadcast(wbuf, root=r)
+        ctx.comm_allgather(wbuf[8 * rank:8 * rank + 8], wbuf)
+        ctx.comm_allreduce_sum(wbuf)
+        ctx.synchronize()
 
     # ---- inputs: rank 0 generates, NCCL broadcast replicates (outside the timed region for `value`)
     d = qcp2_b200.synth_t_inputs_device(ctx, o, v)

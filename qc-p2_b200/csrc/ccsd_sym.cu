@@ -16,7 +16,12 @@
 //  * where a contraction wants T2 or tau-bar with the LAST index free, the antisymmetry t[..,a,f] = -t[..,f,a] supplies
 //    that order for free (cc.cpp:196, :277);
 //  * the T2 equation is assembled in one pass (finalize_t2): <ij||ab> + P(ab) U_ab + P(ij) U_ij + P(ij)P(ab) ring +
-//    unpacked ladder family, divided by D_ijab.
+//    unpacked ladder family, divided by D_ijab;
+//  * spin classes: when every input carries the zero pattern of transform_to_so (integrals.cpp:143-161,
+//    <pq||rs> = 0 unless s_p + s_q = s_r + s_s; checked on the device, exact zeros), a pair (x,y) has class s_x + s_y, every
+//    pair-packed matrix is block diagonal in the class and only the diagonal blocks are stored and multiplied; the
+//    (ov) x (ov) matrices of the ring products are held over class-sorted composites, where each has one non-zero block
+//    per block row.  Without the pattern (the dense synthetic benchmark shape) there is one class and nothing changes.
 #include <cstring>
 #include <vector>
 

@@ -1040,37 +1040,6 @@ void z_t_sub(Ctx &ctx, const double *Z, long long ldz, const double *Ts, int o, 
     ctx.launched("z_t_sub");
 }
 
-__global__ void unpack_add_pairs_kernel(const double *__restrict__ LP, long long npv, int o, int v, double *__restrict__ r) {
-    const long long n = (long long) o * o * v * v;// npv = row stride of LP (>= v(v-1)/2)
-    GRID_STRIDE(lin, n) {
-        long long q = lin;
-        int b = (int) (q % v);
-        q /= v;
-        int a = (int) (q % v);
-        q /= v;
-        int j = (int) (q % o);
-        int i = (int) (q / o);
-        if (i == j || a == b) continue;
-        double sign = 1.0;
-        if (i > j) {
-            const int t = i;
-            i = j, j = t, sign = -sign;
-        }
-        if (a > b) {
-            const int t = a;
-            a = b, b = t, sign = -sign;
-        }
-        const long long pij = (long long) i * o - (long long) i * (i + 1) / 2 + (j - i - 1);
-        const long long pab = (long long) a * v - (long long) a * (a + 1) / 2 + (b - a - 1);
-        r[lin] += sign * LP[pij * npv + pab];
-    }
-}
-void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, double *r) {
-    const long long n = (long long) o * o * v * v;
-    if (n == 0 || o < 2 || v < 2) return;
-    unpack_add_pairs_kernel<<<grid_for(n, kBlock, ctx.sm_count), kBlock, 0, ctx.stream>>>(LP, ld, o, v, r);
-    ctx.launched("unpack_add_pairs");
-}
 
 __global__ void diag_kernel(const double *__restrict__ F, int n, double *__restrict__ d) {
     GRID_STRIDE(i, (long long) n) d[i] = F[i * n + i];

@@ -71,8 +71,6 @@ void ring_tt(Ctx &ctx, const double *Ts, int o, int v, double *out);
 // dst rows are `ld` doubles apart (ld >= d23 (d23-1)/2; an even ld keeps the rows 16-byte aligned for the GEMM's vector copies)
 void pack_pairs(Ctx &ctx, const double *src, int d01, int d23, const int *pairs01, int n01, double *dst, long long ld,
                 PairColMap cm = PairColMap());
-// r[i,j,a,b] += sgn(ij) sgn(ab) LP[p(i,j)][p(a,b)]  (zero on the diagonals); LP is [o(o-1)/2][v(v-1)/2]
-void unpack_add_pairs(Ctx &ctx, const double *LP, long long ld, int o, int v, double *r);
 
 // packed-pair pieces of the fused CCSD iteration (i<j rows, a<b columns; `ld` = row stride, even)
 void tau_pack(Ctx &ctx, const double *Ts, const double *Td, int o, int v, const int *pairs_o, int npo, double *dst, long long ld,

@@ -150,7 +150,12 @@ scf_results RHF(const std::vector<Atom> &atoms, const BasisSet &obs, real_t nele
     DTensor own;
     if (!ao_in) own = eri_ao_tensor(obs), ao_in = &own;
     // hf.cpp:388-399: the SAD guess is taken only for the exact string "STO-3G"; the shipped
-    // inputs use lower case, so every config goes through density_guess
+    // inputs use lower case, so every config goes through density_guess.
+    // The SAD branch (libint2 sto3g_ao_occupation_vector) is not part of this host substrate: with that exact spelling the
+    // SCF would start elsewhere than the reference's, so it is refused instead of silently diverging.
+    if (config.basis == "STO-3G")
+        throw std::invalid_argument("basis \"STO-3G\" selects the reference's SAD guess (hf.cpp:388-392), which this host substrate does "
+                                    "not provide; spell it \"sto-3g\" (the reference's own input.json does) for the core guess");
     Matrix D = density_guess(ndocc, results.nao);
     std::cout << std::endl << "Building initial guess" << std::endl;
     real_t ehf = 0.0;

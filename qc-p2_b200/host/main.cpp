@@ -62,6 +62,10 @@ int main(int argc, char *argv[]) {
         } else if (t == "MP2" || t == "mp2" || t == "CCSD" || t == "ccsd" || t == "CCSD(T)" || t == "ccsd(t)") {
             DTensor ao = eri_ao_tensor(obs);
             scf_results hf;
+            // the reference matches the literal strings only (main.cpp:58,70,80; cc.cpp:39,52): anything else silently runs no
+            // SCF there and continues on uninitialised results -- here it is refused with the reason
+            if (!is_rhf && !is_uhf)
+                throw std::runtime_error("unsupported \"ref\": \"" + config.ref + "\" (use \"RHF\" or \"UHF\", upper case as the reference requires)");
             if (is_rhf) hf = RHF(atoms, obs, nelectron, config, &ao);
             else if (is_uhf) hf = UHF(atoms, obs, nelectron, config, &ao);
             if (!hf.converged) throw std::runtime_error("SCF did not converge within maxiter (the reference leaves its results undefined here)");
